@@ -1,0 +1,228 @@
+/*
+ * ratilqr.h -- C ABI of libratilqr_b200.so
+ *
+ * B200-native (sm_100a) implementation of the data-parallel hot path of
+ * StanfordMSL/RATiLQR.jl: batched iLEQG solves fanned out over risk-sensitivity
+ * samples theta, noisy closed-loop Monte Carlo rollouts, and PETS CEM rollouts.
+ *
+ * The reference is pure Julia and has no FFI seam of its own: the
+ * boundary it offers is its exported Julia API.  Every entry point below therefore
+ * cites the reference function (file:line under the reference tree) that a Julia
+ * `ccall` shim -- or the Python ctypes mirror in ratilqr.jl_b200/ -- replaces with it.
+ *
+ * Conventions
+ *   - plain C, no exceptions; every function returns int32 (0 = ok, <0 = API misuse /
+ *     CUDA error; message from ratilqr_last_error()).
+ *   - NUMERICAL failure is not an error: it is reported per instance in status[b]
+ *     (RATILQR_ST_*) and mapped to value +Inf, exactly where the reference's
+ *     try/catch does (cross_entropy_bilevel_optimization.jl:161-165).
+ *   - all matrices column-major (what Julia produces), instance index slowest.
+ *   - caller owns every host array; the library never keeps a host pointer past return.
+ *   - calls are blocking; one caller thread per ctx; one ctx drives one CUDA device.
+ *   - stage index k is 0-based (optimal_control_problems.jl:28,35).
+ */
+#ifndef RATILQR_H
+#define RATILQR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------
+ * Registered device models (user closures cannot run on the GPU, so the
+ * accelerated path covers a registered set).  Equations: DESIGN.md "Model registry".
+ * ------------------------------------------------------------------------------- */
+enum {
+  RATILQR_MODEL_SINGLE_INTEGRATOR = 1, /* n=2 m=2  x+ = x + dt*u            params [dt]            (test/ileqg_test.jl:12) */
+  RATILQR_MODEL_POWER_LAW         = 2, /* n=2 m=2  x+ = x.^a + u.^b         params [a,b]           (test/ileqg_test.jl:151) */
+  RATILQR_MODEL_DOUBLE_INTEGRATOR = 3, /* n=4 m=2  p+=p+dt*v, v+=v+dt*u     params [dt] */
+  RATILQR_MODEL_PENDULUM          = 4, /* n=2 m=1                           params [dt,g,len,mass,damping] */
+  RATILQR_MODEL_CARTPOLE          = 5, /* n=4 m=1                           params [dt,m_cart,m_pole,len,g] */
+  RATILQR_MODEL_UNICYCLE          = 6, /* n=4 m=2  (px,py,psi,v ; a,omega)  params [dt] */
+  RATILQR_MODEL_QUADROTOR         = 7  /* n=12 m=4                          params [dt,mass,g,Ixx,Iyy,Izz] */
+};
+
+enum {
+  /* c(k,x,u) = (ws0+ws1*k)*(1/2 dx'Q dx + 1/2 u'R u + dx'Pc u) + c0 + c1*k,  dx = x - xg
+   * h(x)     = 1/2 dx'Qf dx + h0
+   * params   = [ws0, ws1, c0, c1, h0, xg(n), Q(n*n), R(m*m), Pc(n*m), Qf(n*n)]  (Q,R,Qf symmetric)
+   * covers optimal_control_problems.jl:59-61, test/ileqg_test.jl:13-14,53-54,68-69 */
+  RATILQR_COST_QUADRATIC  = 1,
+  /* c = sum(x.^p) + sum(u.^p), h = h0 ; params [p, h0]  (test/ileqg_test.jl:152-153) */
+  RATILQR_COST_POWER_LAW  = 2,
+  /* c = sum(abs(u)), h = h0 ; params [h0] ; rollout-only, not differentiable (test/pets_test.jl:16-17) */
+  RATILQR_COST_L1_CONTROL = 3
+};
+
+/* per-instance status (replaces Julia exceptions) */
+enum {
+  RATILQR_ST_OK              = 0,
+  RATILQR_ST_M_NOT_PD_INIT   = 1, /* @assert isposdef(M) inside initialize!           ileqg.jl:234,440 */
+  RATILQR_ST_M_NOT_PD_OPT    = 2, /* @assert isposdef(M) inside solve_approximate_dp! ileqg.jl:366 */
+  RATILQR_ST_DOMAIN          = 3, /* DomainError in the model/cost (negative base of a real power) */
+  RATILQR_ST_LINESEARCH_HANG = 4, /* reference would loop forever: ileqg.jl:526-535 has no eps_min test */
+  RATILQR_ST_MU_OVERFLOW     = 5  /* regularisation restart loop ileqg.jl:359-401 did not terminate */
+};
+
+typedef struct ratilqr_ctx ratilqr_ctx;
+
+/* f, c, h, W, N of FiniteHorizonRiskSensitiveOptimalControlProblem
+ * (optimal_control_problems.jl:67-73), restricted to registered models. */
+typedef struct {
+  int32_t model_id, cost_id;
+  int32_t n, m, N;
+  const double* model_params; int32_t n_model_params;
+  const double* cost_params;  int32_t n_cost_params;     /* length of ONE parameter block */
+  int32_t cost_params_count;                             /* 1 = shared, P = one block per problem */
+  const double* W;                                       /* n*n, or n*n*N when W_time_varying */
+  int32_t W_time_varying;
+} ratilqr_problem_desc;
+
+/* ILEQGSolver keyword arguments, 1:1 with ileqg.jl:165-175,191-194 */
+typedef struct {
+  double  mu_min;            /* 1e-6 */
+  double  delta_0;           /* 2.0  */
+  double  lambda;            /* 0.5  */
+  double  d;                 /* 1e-2 */
+  int32_t iter_max;          /* 100  */
+  int32_t adaptive_eps_init; /* 0    */
+  double  eps_init;          /* 1.0  */
+  double  eps_min;           /* 1e-6 */
+  int32_t f_returns_jacobian;/* accepted for API parity; device Jacobians are always analytic */
+} ratilqr_ileqg_opts;
+
+/* Batch shape: P problems x K theta samples per problem, instance b = p*K + j.
+ * x0 is n*x0_count, u_init is m*N*u_count, with the counts 1 (shared) or P. */
+typedef struct {
+  int32_t P, K;
+  const double* x0;     int32_t x0_count;
+  const double* u_init; int32_t u_count;
+  const double* theta;  /* P*K */
+} ratilqr_batch_in;
+
+/* Any pointer may be NULL (output skipped, nothing copied back). B = P*K. */
+typedef struct {
+  double*  x;          /* n*(N+1)*B   x_array          ileqg.jl:655 */
+  double*  l;          /* m*N*B       l_array */
+  double*  L;          /* m*n*N*B     L_array */
+  double*  value;      /* B           value_current (+Inf when status != 0) */
+  int32_t* status;     /* B */
+  int32_t* iters;      /* B  iter_current */
+  int32_t* trials;     /* B  line-search merit evaluations (entries of eps_history) */
+  int32_t* restarts;   /* B  calls of increase_mu_and_delta! */
+  double*  mu;         /* B  final mu */
+  double*  d_current;  /* B  final d_current */
+  double*  eps_hist;   /* 2*eps_hist_cap*B  (eps, new-cur) pairs     ileqg.jl:537 */
+  int32_t  eps_hist_cap;
+} ratilqr_ileqg_out;
+
+/* ---- context ------------------------------------------------------------------ */
+int32_t ratilqr_create(ratilqr_ctx** ctx, int32_t device_id);
+int32_t ratilqr_destroy(ratilqr_ctx* ctx);
+const char* ratilqr_last_error(const ratilqr_ctx* ctx);
+int32_t ratilqr_version(void);
+/* static description of a registered model: dims and parameter counts (0 if unknown id) */
+int32_t ratilqr_model_dims(int32_t model_id, int32_t* n, int32_t* m, int32_t* n_params);
+int32_t ratilqr_cost_param_count(int32_t cost_id, int32_t n, int32_t m);
+
+/* ---- the hot path: solve!(::ILEQGSolver, ...) for a whole batch ------------------
+ * replaces ileqg.jl:635-659 (initialize! :214-236, step! :598-613, solve_approximate_dp!
+ * :341-406, line_search! :494-592) run once per instance; one persistent kernel. */
+int32_t ratilqr_ileqg_solve_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc,
+                                  const ratilqr_ileqg_opts* opts,
+                                  const ratilqr_batch_in* in, ratilqr_ileqg_out* out);
+
+/* compute_cost / compute_cost_serial of RAT iLQR (cross_entropy_bilevel_optimization.jl
+ * :173-227) and compute_cost_worker of RAT iLQR++ (nelder_mead_bilevel_optimization.jl
+ * :134-158):  cost[b] = value[b] + kl_bound/theta[b], +Inf on any failure. */
+int32_t ratilqr_ce_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc,
+                         const ratilqr_ileqg_opts* opts, const ratilqr_batch_in* in,
+                         double kl_bound, double* cost, int32_t* status);
+
+/* Device-resident variant used for throughput measurement: stage once, run many times.
+ * stage = H2D of inputs; run = the solve kernel only, `reps` launches back to back on the
+ * ctx stream, bracketed by CUDA events recorded on that stream (ms_total out);
+ * fetch = D2H of whatever `out` asks for. */
+int32_t ratilqr_ileqg_stage(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc,
+                            const ratilqr_ileqg_opts* opts, const ratilqr_batch_in* in);
+int32_t ratilqr_ileqg_run(ratilqr_ctx* ctx, int32_t reps, float* ms_total);
+int32_t ratilqr_ileqg_fetch(ratilqr_ctx* ctx, ratilqr_ileqg_out* out);
+
+/* ---- component kernels, exposed for unit parity -------------------- */
+/* simulate_dynamics open loop (ileqg.jl:18-38): x0 n*B, u m*N*B -> x n*(N+1)*B */
+int32_t ratilqr_rollout_open_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t B,
+                                   const double* x0, const double* u, double* x, int32_t* status);
+/* simulate_dynamics closed loop (ileqg.jl:62-87): -> x_new n*(N+1)*B, u_new m*N*B */
+int32_t ratilqr_rollout_closed_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t B,
+                                     const double* xbar, const double* l, const double* L,
+                                     double* x_new, double* u_new, int32_t* status);
+/* integrate_cost (ileqg.jl:115-124) */
+int32_t ratilqr_integrate_cost_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t B,
+                                     const double* x, const double* u, double* cost, int32_t* status);
+/* approximate_model (ileqg.jl:258-322): per instance q (N+1), qv n*(N+1), Q n*n*(N+1),
+ * r m*N, R m*m*N, Pm m*n*N, A n*n*N, Bm n*m*N */
+int32_t ratilqr_linearize_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t B,
+                                const double* x, const double* u,
+                                double* q, double* qv, double* Q, double* r, double* R,
+                                double* Pm, double* A, double* Bm, int32_t* status);
+/* the two Riccati passes on caller-supplied approximations (any n<=12, m<=4 registered size):
+ * optimise != 0 : solve_approximate_dp! (ileqg.jl:341-406); L, dl are outputs; mu/delta in-out
+ * optimise == 0 : solve_approximate_dp  (ileqg.jl:412-465); L input, dl input or NULL (zeros)
+ * W is n*n (shared). outputs s (N+1)*B, sv n*(N+1)*B, S n*n*(N+1)*B. */
+int32_t ratilqr_riccati_batch(ratilqr_ctx* ctx, int32_t n, int32_t m, int32_t N, int32_t B,
+                              int32_t optimise,
+                              const double* q, const double* qv, const double* Q, const double* r,
+                              const double* R, const double* Pm, const double* A, const double* Bm,
+                              const double* W, const double* theta,
+                              double mu_min, double delta_0, double* mu, double* delta,
+                              double* L, double* dl,
+                              double* s, double* sv, double* S, int32_t* status, int32_t* restarts);
+
+/* ---- noisy closed-loop Monte Carlo rollouts ----------------------------------------
+ * simulate_dynamics(problem, x_array, l_array, L_array, rng) + integrate_cost
+ * (ileqg.jl:94-109,115-124) for n_samples noise realisations of ONE policy per problem.
+ * noise: injected w tensor n*N*n_samples (per problem: n*N*n_samples*P) or NULL -> Philox(seed)
+ * coloured with chol(W).  J n_samples*P.  stats per problem: [mean, var(unbiased),
+ * entropic risk 1/theta*log mean exp(theta J) (theta_risk>0)]. */
+int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t P,
+                           const double* xbar, const double* l, const double* L,
+                           int32_t n_samples, const double* noise, uint64_t seed,
+                           double theta_risk, double* J, double* stats, double* x_out);
+
+/* ---- PETS (pets.jl) ---------------------------------------------------------------- */
+typedef struct {
+  int32_t noise_kind;       /* 0 gaussian chol(W)*z ; 1 uniform[0,1)*scale (test/pets_test.jl:15) */
+  double  noise_scale;
+  int32_t n_ensemble;       /* model parameter sets; particle kk uses set kk / (particles/n_ensemble) */
+  const double* ensemble_params; /* n_model_params * n_ensemble, or NULL -> desc.model_params */
+} ratilqr_generative_desc;
+
+/* compute_cost_serial (pets.jl:128-157): controls m*N*C, noise n*N*particles*C or NULL->Philox */
+int32_t ratilqr_pets_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc,
+                           const ratilqr_generative_desc* gen, const double* x0,
+                           const double* controls, int32_t C, int32_t particles,
+                           const double* noise, uint64_t seed, double* cost);
+/* get_elite_samples + compute_new_distribution (pets.jl:159-191) on device */
+int32_t ratilqr_pets_refit(ratilqr_ctx* ctx, int32_t m, int32_t N, int32_t C, int32_t num_elite,
+                           double smoothing, const double* controls, const double* cost,
+                           double* mu, double* Sigma, int32_t* elite_idx);
+/* step!/solve! (pets.jl:193-245,270-281): whole CEM loop on device. z_inject: m*N*C*iter_max
+ * standard-normal draws or NULL -> Philox(seed). mu m*N, Sigma m*m*N are in-out. */
+int32_t ratilqr_pets_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc,
+                           const ratilqr_generative_desc* gen, const double* x0,
+                           int32_t C, int32_t particles, int32_t num_elite, int32_t iter_max,
+                           double smoothing, const double* z_inject, const double* noise,
+                           uint64_t seed, double* mu, double* Sigma);
+
+/* ---- measurement utilities --------------------------------------------------------- */
+/* dependent-chain-free DFMA loop on every SM: returns achieved TFLOP/s (FP64, non-tensor) */
+int32_t ratilqr_fp64_peak_probe(ratilqr_ctx* ctx, double* tflops, float* ms);
+/* number of kernel launches issued by this ctx since creation */
+int64_t ratilqr_launch_count(const ratilqr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RATILQR_H */

@@ -1,0 +1,369 @@
+"""ctypes view of the C ABI declared in include/ratilqr.h.
+
+`CApi(cdll, prefix)` binds the entry points `<prefix>ileqg_solve_batch`, ... of a shared
+library and wraps them in numpy-friendly methods.  The product binds prefix ``ratilqr_`` of
+libratilqr_b200.so (see _lib.py).  The same class is reused by the test-suite to drive the
+CPU oracle (prefix ``oracle_``) so that one harness feeds both sides identical inputs.
+
+All arrays are Fortran-ordered (column-major, instance index slowest), i.e. exactly what the
+Julia shim passes (julia/RATiLQRB200.jl).
+"""
+import ctypes as C
+
+import numpy as np
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class ProblemDesc(C.Structure):  # ratilqr_problem_desc
+    _fields_ = [
+        ("model_id", C.c_int32), ("cost_id", C.c_int32),
+        ("n", C.c_int32), ("m", C.c_int32), ("N", C.c_int32),
+        ("model_params", c_double_p), ("n_model_params", C.c_int32),
+        ("cost_params", c_double_p), ("n_cost_params", C.c_int32),
+        ("cost_params_count", C.c_int32),
+        ("W", c_double_p), ("W_time_varying", C.c_int32),
+    ]
+
+
+class IleqgOpts(C.Structure):  # ratilqr_ileqg_opts  (ileqg.jl:165-175)
+    _fields_ = [
+        ("mu_min", C.c_double), ("delta_0", C.c_double), ("lam", C.c_double), ("d", C.c_double),
+        ("iter_max", C.c_int32), ("adaptive_eps_init", C.c_int32),
+        ("eps_init", C.c_double), ("eps_min", C.c_double), ("f_returns_jacobian", C.c_int32),
+    ]
+
+
+class BatchIn(C.Structure):  # ratilqr_batch_in
+    _fields_ = [
+        ("P", C.c_int32), ("K", C.c_int32),
+        ("x0", c_double_p), ("x0_count", C.c_int32),
+        ("u_init", c_double_p), ("u_count", C.c_int32),
+        ("theta", c_double_p),
+    ]
+
+
+class IleqgOut(C.Structure):  # ratilqr_ileqg_out
+    _fields_ = [
+        ("x", c_double_p), ("l", c_double_p), ("L", c_double_p), ("value", c_double_p),
+        ("status", c_int32_p), ("iters", c_int32_p), ("trials", c_int32_p), ("restarts", c_int32_p),
+        ("mu", c_double_p), ("d_current", c_double_p),
+        ("eps_hist", c_double_p), ("eps_hist_cap", C.c_int32),
+    ]
+
+
+class GenerativeDesc(C.Structure):  # ratilqr_generative_desc
+    _fields_ = [
+        ("noise_kind", C.c_int32), ("noise_scale", C.c_double),
+        ("n_ensemble", C.c_int32), ("ensemble_params", c_double_p),
+    ]
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_int32_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F"))
+
+
+class ApiError(RuntimeError):
+    pass
+
+
+ILEQG_DEFAULTS = dict(mu_min=1e-6, delta_0=2.0, lam=0.5, d=1e-2, iter_max=100,
+                      adaptive_eps_init=False, eps_init=1.0, eps_min=1e-6, f_returns_jacobian=False)
+
+
+def make_opts(**kw):
+    o = dict(ILEQG_DEFAULTS)
+    o.update(kw)
+    return IleqgOpts(o["mu_min"], o["delta_0"], o["lam"], o["d"], int(o["iter_max"]),
+                     int(bool(o["adaptive_eps_init"])), o["eps_init"], o["eps_min"],
+                     int(bool(o["f_returns_jacobian"])))
+
+
+class Spec:
+    """Plain description of a registered problem: what ratilqr_problem_desc carries."""
+
+    def __init__(self, model_id, cost_id, n, m, N, model_params, cost_params, W, cost_params_count=1):
+        self.model_id, self.cost_id, self.n, self.m, self.N = int(model_id), int(cost_id), int(n), int(m), int(N)
+        self.model_params = _f64(model_params)
+        cp = np.asarray(cost_params, dtype=np.float64)
+        if cp.ndim == 2:  # (P, n_cost_params): one parameter block per problem
+            cost_params_count = cp.shape[0]
+        self.cost_params_count = int(cost_params_count)
+        self.cost_params = np.ascontiguousarray(cp.reshape(-1))
+        self.n_cost_params = self.cost_params.size // self.cost_params_count
+        W = np.asarray(W, dtype=np.float64)
+        self.W_time_varying = int(W.ndim == 3)
+        # time-varying W is given as (N, n, n); each block stored column-major
+        self.W = np.ascontiguousarray(np.stack([w.ravel(order="F") for w in W]).ravel()) if W.ndim == 3 else _f64(W)
+
+    def desc(self):
+        d = ProblemDesc(self.model_id, self.cost_id, self.n, self.m, self.N,
+                        _dp(self.model_params), self.model_params.size,
+                        _dp(self.cost_params), self.n_cost_params, self.cost_params_count,
+                        _dp(self.W), self.W_time_varying)
+        return d
+
+
+class CApi:
+    def __init__(self, cdll, prefix, needs_ctx):
+        self.dll, self.prefix, self.needs_ctx = cdll, prefix, needs_ctx
+        self.ctx = C.c_void_p(None)
+        self._bind()
+        if needs_ctx:
+            self._create = getattr(cdll, prefix + "create")
+            self._create.restype = C.c_int32
+            self._create.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
+            self._destroy = getattr(cdll, prefix + "destroy")
+            self._destroy.argtypes = [C.c_void_p]
+            self._last_error = getattr(cdll, prefix + "last_error")
+            self._last_error.restype = C.c_char_p
+            self._last_error.argtypes = [C.c_void_p]
+
+    # -- binding --------------------------------------------------------------------------
+    def _fn(self, name, argtypes, restype=C.c_int32):
+        f = getattr(self.dll, self.prefix + name)
+        f.restype = restype
+        f.argtypes = argtypes
+        return f
+
+    def _bind(self):
+        vp = C.c_void_p
+        PD, IO, BI, OUT, GD = (C.POINTER(ProblemDesc), C.POINTER(IleqgOpts), C.POINTER(BatchIn),
+                               C.POINTER(IleqgOut), C.POINTER(GenerativeDesc))
+        dp, ip, i32, f64 = c_double_p, c_int32_p, C.c_int32, C.c_double
+        self.f_solve = self._fn("ileqg_solve_batch", [vp, PD, IO, BI, OUT])
+        self.f_ce_costs = self._fn("ce_costs", [vp, PD, IO, BI, f64, dp, ip])
+        self.f_open = self._fn("rollout_open_batch", [vp, PD, i32, dp, dp, dp, ip])
+        self.f_closed = self._fn("rollout_closed_batch", [vp, PD, i32, dp, dp, dp, dp, dp, ip])
+        self.f_cost = self._fn("integrate_cost_batch", [vp, PD, i32, dp, dp, dp, ip])
+        self.f_lin = self._fn("linearize_batch", [vp, PD, i32, dp, dp] + [dp] * 8 + [ip])
+        self.f_ric = self._fn("riccati_batch", [vp, i32, i32, i32, i32, i32] + [dp] * 8 + [dp, dp, f64, f64, dp, dp,
+                                                                                          dp, dp, dp, dp, dp, ip, ip])
+        self.f_mc = self._fn("mc_rollout", [vp, PD, i32, dp, dp, dp, i32, dp, C.c_uint64, f64, dp, dp, dp])
+        self.f_pets_costs = self._fn("pets_costs", [vp, PD, GD, dp, dp, i32, i32, dp, C.c_uint64, dp])
+        self.f_pets_refit = self._fn("pets_refit", [vp, i32, i32, i32, i32, f64, dp, dp, dp, dp, ip])
+        self.f_pets_solve = self._fn("pets_solve", [vp, PD, GD, dp, i32, i32, i32, i32, f64, dp, dp, C.c_uint64, dp, dp])
+
+    def open(self, device_id=0):
+        if self.needs_ctx and not self.ctx:
+            rc = self._create(C.byref(self.ctx), device_id)
+            if rc != 0:
+                raise ApiError(f"{self.prefix}create failed with code {rc}")
+        return self
+
+    def close(self):
+        if self.needs_ctx and self.ctx:
+            self._destroy(self.ctx)
+            self.ctx = C.c_void_p(None)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = ""
+            if self.needs_ctx and self.ctx:
+                m = self._last_error(self.ctx)
+                msg = m.decode() if m else ""
+            raise ApiError(f"{self.prefix}{what} failed with code {rc}: {msg}")
+
+    # -- wrappers --------------------------------------------------------------------------
+    @staticmethod
+    def _batch(spec, x0, u_init, theta, P=None):
+        n, m, N = spec.n, spec.m, spec.N
+        theta = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
+        x0 = np.asarray(x0, dtype=np.float64)
+        u_init = np.asarray(u_init, dtype=np.float64)
+        x0_count = 1 if x0.ndim == 1 else x0.shape[-1]
+        u_count = 1 if u_init.ndim == 2 else u_init.shape[-1]
+        if P is None:
+            P = max(x0_count, u_count, spec.cost_params_count)
+        assert theta.size % P == 0, "theta count must be a multiple of the problem count"
+        K = theta.size // P
+        assert x0.shape[0] == n and u_init.shape[0] == m and u_init.shape[1] == N
+        x0f, uf = _f64(x0), _f64(u_init)
+        bi = BatchIn(P, K, _dp(x0f), x0_count, _dp(uf), u_count, _dp(theta))
+        return bi, (x0f, uf, theta)
+
+    def ileqg_solve_batch(self, spec, x0, u_init, theta, opts=None, want=("x", "l", "L"), eps_hist_cap=0, P=None):
+        """solve!(::ILEQGSolver, ...) for a batch (ileqg.jl:635-659). Returns a dict of arrays."""
+        opts = opts or make_opts()
+        n, m, N = spec.n, spec.m, spec.N
+        bi, keep = self._batch(spec, x0, u_init, theta, P)
+        B = bi.P * bi.K
+        res = dict(value=np.empty(B), status=np.empty(B, np.int32), iters=np.empty(B, np.int32),
+                   trials=np.empty(B, np.int32), restarts=np.empty(B, np.int32), mu=np.empty(B),
+                   d_current=np.empty(B))
+        if "x" in want:
+            res["x"] = np.zeros((n, N + 1, B), order="F")
+        if "l" in want:
+            res["l"] = np.zeros((m, N, B), order="F")
+        if "L" in want:
+            res["L"] = np.zeros((m, n, N, B), order="F")
+        if eps_hist_cap:
+            res["eps_hist"] = np.zeros((2, eps_hist_cap, B), order="F")
+        out = IleqgOut(_dp(res.get("x")), _dp(res.get("l")), _dp(res.get("L")), _dp(res["value"]),
+                       _ip(res["status"]), _ip(res["iters"]), _ip(res["trials"]), _ip(res["restarts"]),
+                       _dp(res["mu"]), _dp(res["d_current"]), _dp(res.get("eps_hist")), eps_hist_cap)
+        d = spec.desc()
+        self._check(self.f_solve(self.ctx, C.byref(d), C.byref(opts), C.byref(bi), C.byref(out)), "ileqg_solve_batch")
+        return res
+
+    def ce_costs(self, spec, x0, u_init, theta, kl_bound, opts=None, P=None):
+        """compute_cost (cross_entropy_bilevel_optimization.jl:173-195)."""
+        opts = opts or make_opts()
+        bi, keep = self._batch(spec, x0, u_init, theta, P)
+        B = bi.P * bi.K
+        cost, status = np.empty(B), np.empty(B, np.int32)
+        d = spec.desc()
+        self._check(self.f_ce_costs(self.ctx, C.byref(d), C.byref(opts), C.byref(bi), float(kl_bound),
+                                    _dp(cost), _ip(status)), "ce_costs")
+        return cost, status
+
+    def rollout_open(self, spec, x0, u):
+        n, m, N = spec.n, spec.m, spec.N
+        x0 = np.asarray(x0, dtype=np.float64).reshape(n, -1)
+        B = x0.shape[1]
+        u = np.asarray(u, dtype=np.float64).reshape(m, N, B)
+        x = np.zeros((n, N + 1, B), order="F")
+        st = np.zeros(B, np.int32)
+        d = spec.desc()
+        x0f, uf = _f64(x0), _f64(u)
+        self._check(self.f_open(self.ctx, C.byref(d), B, _dp(x0f), _dp(uf), _dp(x), _ip(st)), "rollout_open_batch")
+        return x, st
+
+    def rollout_closed(self, spec, xbar, l, L):
+        n, m, N = spec.n, spec.m, spec.N
+        xbar = np.asarray(xbar, dtype=np.float64).reshape(n, N + 1, -1)
+        B = xbar.shape[2]
+        lf, Lf, xf = _f64(np.asarray(l).reshape(m, N, B)), _f64(np.asarray(L).reshape(m, n, N, B)), _f64(xbar)
+        xn = np.zeros((n, N + 1, B), order="F")
+        un = np.zeros((m, N, B), order="F")
+        st = np.zeros(B, np.int32)
+        d = spec.desc()
+        self._check(self.f_closed(self.ctx, C.byref(d), B, _dp(xf), _dp(lf), _dp(Lf), _dp(xn), _dp(un), _ip(st)),
+                    "rollout_closed_batch")
+        return xn, un, st
+
+    def integrate_cost(self, spec, x, u):
+        n, m, N = spec.n, spec.m, spec.N
+        x = np.asarray(x, dtype=np.float64).reshape(n, N + 1, -1)
+        B = x.shape[2]
+        xf, uf = _f64(x), _f64(np.asarray(u).reshape(m, N, B))
+        cost = np.zeros(B)
+        st = np.zeros(B, np.int32)
+        d = spec.desc()
+        self._check(self.f_cost(self.ctx, C.byref(d), B, _dp(xf), _dp(uf), _dp(cost), _ip(st)), "integrate_cost_batch")
+        return cost, st
+
+    def linearize(self, spec, x, u):
+        """approximate_model (ileqg.jl:258-322)."""
+        n, m, N = spec.n, spec.m, spec.N
+        x = np.asarray(x, dtype=np.float64).reshape(n, N + 1, -1)
+        B = x.shape[2]
+        xf, uf = _f64(x), _f64(np.asarray(u).reshape(m, N, B))
+        r = dict(q=np.zeros((N + 1, B), order="F"), qv=np.zeros((n, N + 1, B), order="F"),
+                 Q=np.zeros((n, n, N + 1, B), order="F"), r=np.zeros((m, N, B), order="F"),
+                 R=np.zeros((m, m, N, B), order="F"), P=np.zeros((m, n, N, B), order="F"),
+                 A=np.zeros((n, n, N, B), order="F"), B=np.zeros((n, m, N, B), order="F"))
+        st = np.zeros(B, np.int32)
+        d = spec.desc()
+        self._check(self.f_lin(self.ctx, C.byref(d), B, _dp(xf), _dp(uf), _dp(r["q"]), _dp(r["qv"]), _dp(r["Q"]),
+                               _dp(r["r"]), _dp(r["R"]), _dp(r["P"]), _dp(r["A"]), _dp(r["B"]), _ip(st)),
+                    "linearize_batch")
+        r["status"] = st
+        return r
+
+    def riccati(self, lin, W, theta, optimise, L=None, dl=None, mu=0.0, delta=2.0, mu_min=1e-6, delta_0=2.0):
+        """solve_approximate_dp! (optimise) / solve_approximate_dp (evaluate) on given approximations."""
+        n, N1, B = lin["qv"].shape
+        N = N1 - 1
+        m = lin["r"].shape[0]
+        theta = np.ascontiguousarray(np.broadcast_to(np.asarray(theta, dtype=np.float64), (B,)))
+        mu_a = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, dtype=np.float64), (B,))).copy()
+        de_a = np.ascontiguousarray(np.broadcast_to(np.asarray(delta, dtype=np.float64), (B,))).copy()
+        Wf = _f64(W)
+        arrs = [_f64(lin[k]) for k in ("q", "qv", "Q", "r", "R", "P", "A", "B")]
+        if optimise:
+            Lf = np.zeros(m * n * N * B)
+            dlf = np.zeros(m * N * B)
+        else:
+            Lf = _f64(np.asarray(L).reshape(m, n, N, B)).copy()
+            dlf = None if dl is None else _f64(np.asarray(dl).reshape(m, N, B)).copy()
+        s = np.zeros((N + 1, B), order="F")
+        sv = np.zeros((n, N + 1, B), order="F")
+        S = np.zeros((n, n, N + 1, B), order="F")
+        st = np.zeros(B, np.int32)
+        rs = np.zeros(B, np.int32)
+        self._check(self.f_ric(self.ctx, n, m, N, B, int(optimise), *[_dp(a) for a in arrs], _dp(Wf), _dp(theta),
+                               float(mu_min), float(delta_0), _dp(mu_a), _dp(de_a), _dp(Lf), _dp(dlf),
+                               _dp(s), _dp(sv), _dp(S), _ip(st), _ip(rs)), "riccati_batch")
+        return dict(s=s, sv=sv, S=S, status=st, restarts=rs, mu=mu_a, delta=de_a,
+                    L=Lf.reshape((m, n, N, B), order="F"),
+                    dl=None if dlf is None else dlf.reshape((m, N, B), order="F"))
+
+    def mc_rollout(self, spec, xbar, l, L, n_samples, noise=None, seed=0, theta_risk=0.0, want_x=False, P=1):
+        n, m, N = spec.n, spec.m, spec.N
+        xf, lf, Lf = _f64(xbar), _f64(l), _f64(L)
+        nf = None if noise is None else _f64(noise)
+        J = np.zeros(n_samples * P)
+        stats = np.zeros(3 * P)
+        xo = np.zeros((n, N + 1, n_samples * P), order="F") if want_x else None
+        d = spec.desc()
+        self._check(self.f_mc(self.ctx, C.byref(d), P, _dp(xf), _dp(lf), _dp(Lf), n_samples, _dp(nf), int(seed),
+                              float(theta_risk), _dp(J), _dp(stats), _dp(xo)), "mc_rollout")
+        return dict(J=J, stats=stats.reshape(P, 3), x=xo)
+
+    @staticmethod
+    def _gen(gen):
+        gen = gen or {}
+        ens = gen.get("ensemble_params")
+        ensf = None if ens is None else _f64(ens)
+        g = GenerativeDesc(int(gen.get("noise_kind", 0)), float(gen.get("noise_scale", 1.0)),
+                           int(gen.get("n_ensemble", 1)), _dp(ensf))
+        return g, ensf
+
+    def pets_costs(self, spec, x0, controls, particles, noise=None, seed=0, gen=None):
+        """compute_cost_serial (pets.jl:128-157). controls (m, N, C)."""
+        m, N = spec.m, spec.N
+        controls = np.asarray(controls, dtype=np.float64).reshape(m, N, -1)
+        Cn = controls.shape[2]
+        cf, x0f = _f64(controls), _f64(x0)
+        nf = None if noise is None else _f64(noise)
+        cost = np.zeros(Cn)
+        g, keep = self._gen(gen)
+        d = spec.desc()
+        self._check(self.f_pets_costs(self.ctx, C.byref(d), C.byref(g), _dp(x0f), _dp(cf), Cn, int(particles),
+                                      _dp(nf), int(seed), _dp(cost)), "pets_costs")
+        return cost
+
+    def pets_refit(self, controls, cost, num_elite, smoothing, mu, Sigma):
+        """get_elite_samples + compute_new_distribution (pets.jl:159-191)."""
+        controls = np.asarray(controls, dtype=np.float64)
+        m, N, Cn = controls.shape
+        cf, costf = _f64(controls), _f64(cost)
+        mu_o, Sg_o = _f64(mu).copy(), _f64(Sigma).copy()
+        idx = np.zeros(num_elite, np.int32)
+        self._check(self.f_pets_refit(self.ctx, m, N, Cn, int(num_elite), float(smoothing), _dp(cf), _dp(costf),
+                                      _dp(mu_o), _dp(Sg_o), _ip(idx)), "pets_refit")
+        return mu_o.reshape((m, N), order="F"), Sg_o.reshape((m, m, N), order="F"), idx
+
+    def pets_solve(self, spec, x0, mu, Sigma, C_samples, particles, num_elite, iter_max, smoothing,
+                   z_inject=None, noise=None, seed=0, gen=None):
+        m, N = spec.m, spec.N
+        x0f = _f64(x0)
+        mu_o, Sg_o = _f64(mu).copy(), _f64(Sigma).copy()
+        zf = None if z_inject is None else _f64(z_inject)
+        nf = None if noise is None else _f64(noise)
+        g, keep = self._gen(gen)
+        d = spec.desc()
+        self._check(self.f_pets_solve(self.ctx, C.byref(d), C.byref(g), _dp(x0f), int(C_samples), int(particles),
+                                      int(num_elite), int(iter_max), float(smoothing), _dp(zf), _dp(nf), int(seed),
+                                      _dp(mu_o), _dp(Sg_o)), "pets_solve")
+        return mu_o.reshape((m, N), order="F"), Sg_o.reshape((m, m, N), order="F")
