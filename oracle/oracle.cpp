@@ -388,7 +388,7 @@ bool riccati_stage(int n, int m, bool optimise, double theta, double mu,
                    double q, const double* qv, const double* Q, const double* r, const double* R,
                    const double* P, const double* A, const double* B,
                    double* L, double* dl, double* s, double* sv, double* S) {
-  vec DS(n * n), Dsv(n);
+  double DS[144], Dsv[12];
   double extra;
   if (theta == 0.0) {  // ileqg.jl:384-385 (D = I)
     for (int i = 0; i < n * n; ++i) DS[i] = Sp[i];
@@ -400,10 +400,10 @@ bool riccati_stage(int n, int m, bool optimise, double theta, double mu,
     }
     extra = 0.5 * tr;
   } else {
-    vec M(n * n), C(n * n), invd(n), Z(n * n), z(n);
+    double M[144], C[144], invd[12], Z[144], z[12];
     for (int i = 0; i < n * n; ++i) M[i] = Winv[i] - theta * Sp[i];  // :365
     double detM;
-    if (!chol_lower(n, M.data(), C.data(), invd.data(), &detM)) throw NotPosDef();  // :366
+    if (!chol_lower(n, M, C, invd, &detM)) throw NotPosDef();  // :366
     // Z = C^-1 Sp, z = C^-1 svp  =>  Sp M^-1 Sp = Z'Z ;  D*Sp = Sp + theta Z'Z  (:367)
     for (int c = 0; c < n; ++c)
       for (int i = 0; i < n; ++i) {
@@ -423,16 +423,16 @@ bool riccati_stage(int n, int m, bool optimise, double theta, double mu,
         DS[i + j * n] = v;
         DS[j + i * n] = v;
       }
-    for (int i = 0; i < n; ++i) Dsv[i] = FMA(theta, dotp(n, &Z[i * n], 1, z.data(), 1), svp[i]);
-    double quad = dotp(n, z.data(), 1, z.data(), 1);
+    for (int i = 0; i < n; ++i) Dsv[i] = FMA(theta, dotp(n, &Z[i * n], 1, z, 1), svp[i]);
+    double quad = dotp(n, z, 1, z, 1);
     extra = (theta / 2) * quad - (1 / (2 * theta)) * std::log(detW * detM);  // :387
   }
-  vec T(n * n), U(n * m), g(m), G(m * n), H(m * m);
+  double T[144], U[48], g[4], G[48], H[16];
   for (int j = 0; j < n; ++j)
     for (int i = 0; i < n; ++i) T[i + j * n] = dotp(n, &DS[i], n, A + j * n, 1);
   for (int j = 0; j < m; ++j)
     for (int i = 0; i < n; ++i) U[i + j * n] = dotp(n, &DS[i], n, B + j * n, 1);
-  for (int i = 0; i < m; ++i) g[i] = r[i] + dotp(n, B + i * n, 1, Dsv.data(), 1);  // :368
+  for (int i = 0; i < m; ++i) g[i] = r[i] + dotp(n, B + i * n, 1, Dsv, 1);  // :368
   for (int j = 0; j < n; ++j)
     for (int i = 0; i < m; ++i) G[i + j * m] = P[i + j * m] + dotp(n, B + i * n, 1, &T[j * n], 1);  // :369
   for (int i = 0; i < m; ++i)
@@ -443,12 +443,12 @@ bool riccati_stage(int n, int m, bool optimise, double theta, double mu,
       H[j + i * m] = h;
     }
   if (optimise) {
-    vec CH(m * m), invh(m);
-    if (!chol_lower(m, H.data(), CH.data(), invh.data(), nullptr)) return false;  // :372
+    double CH[16], invh[4];
+    if (!chol_lower(m, H, CH, invh, nullptr)) return false;  // :372
     // L = -H\G ; dl = -H\g  (:379-382)
     for (int c = 0; c <= n; ++c) {
       double y[4];
-      const double* rhs = (c < n) ? &G[c * m] : g.data();
+      const double* rhs = (c < n) ? &G[c * m] : g;
       for (int i = 0; i < m; ++i) {
         double a = rhs[i];
         for (int k = 0; k < i; ++k) a = FMA(-CH[i + k * m], y[k], a);
@@ -464,19 +464,19 @@ bool riccati_stage(int n, int m, bool optimise, double theta, double mu,
       }
     }
   }
-  vec HL(m * n), Hdl(m);
+  double HL[48], Hdl[4];
   for (int j = 0; j < n; ++j)
     for (int i = 0; i < m; ++i) HL[i + j * m] = dotp(m, &H[i], m, L + j * m, 1);
   double sval = q + sp;  // :383 / :452
   if (dl) {
     for (int i = 0; i < m; ++i) Hdl[i] = dotp(m, &H[i], m, dl, 1);
-    sval = (sval + 0.5 * dotp(m, dl, 1, Hdl.data(), 1)) + dotp(m, dl, 1, g.data(), 1);
+    sval = (sval + 0.5 * dotp(m, dl, 1, Hdl, 1)) + dotp(m, dl, 1, g, 1);
   }
   *s = sval + extra;
   for (int i = 0; i < n; ++i) {  // :389 / :458
-    double a = qv[i] + dotp(n, A + i * n, 1, Dsv.data(), 1);
-    if (dl) a = a + dotp(m, L + i * m, 1, Hdl.data(), 1);
-    a = a + dotp(m, L + i * m, 1, g.data(), 1);
+    double a = qv[i] + dotp(n, A + i * n, 1, Dsv, 1);
+    if (dl) a = a + dotp(m, L + i * m, 1, Hdl, 1);
+    a = a + dotp(m, L + i * m, 1, g, 1);
     if (dl) a = a + dotp(m, &G[i * m], 1, dl, 1);
     sv[i] = a;
   }

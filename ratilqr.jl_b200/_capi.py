@@ -130,7 +130,12 @@ class CApi:
 
     # -- binding --------------------------------------------------------------------------
     def _fn(self, name, argtypes, restype=C.c_int32):
-        f = getattr(self.dll, self.prefix + name)
+        try:
+            f = getattr(self.dll, self.prefix + name)
+        except AttributeError:  # partial providers (the test-only host emulation) lack some entry points
+            def missing(*a, **k):
+                raise ApiError(f"{self.prefix}{name} is not exported by this library")
+            return missing
         f.restype = restype
         f.argtypes = argtypes
         return f
@@ -151,6 +156,11 @@ class CApi:
         self.f_mc = self._fn("mc_rollout", [vp, PD, i32, dp, dp, dp, i32, dp, C.c_uint64, f64, dp, dp, dp])
         self.f_pets_costs = self._fn("pets_costs", [vp, PD, GD, dp, dp, i32, i32, dp, C.c_uint64, dp])
         self.f_pets_refit = self._fn("pets_refit", [vp, i32, i32, i32, i32, f64, dp, dp, dp, dp, ip])
+        self.f_stage = self._fn("ileqg_stage", [vp, PD, IO, BI])
+        self.f_run = self._fn("ileqg_run", [vp, i32, C.POINTER(C.c_float)])
+        self.f_fetch = self._fn("ileqg_fetch", [vp, OUT])
+        self.f_probe = self._fn("fp64_peak_probe", [vp, dp, C.POINTER(C.c_float)])
+        self.f_launches = self._fn("launch_count", [vp], restype=C.c_int64)
         self.f_pets_solve = self._fn("pets_solve", [vp, PD, GD, dp, i32, i32, i32, i32, f64, dp, dp, C.c_uint64, dp, dp])
 
     def open(self, device_id=0):
@@ -214,6 +224,47 @@ class CApi:
         d = spec.desc()
         self._check(self.f_solve(self.ctx, C.byref(d), C.byref(opts), C.byref(bi), C.byref(out)), "ileqg_solve_batch")
         return res
+
+    # device-resident variant (throughput measurement): stage once, run many, fetch
+    def stage(self, spec, x0, u_init, theta, opts=None, P=None):
+        opts = opts or make_opts()
+        bi, keep = self._batch(spec, x0, u_init, theta, P)
+        d = spec.desc()
+        self._check(self.f_stage(self.ctx, C.byref(d), C.byref(opts), C.byref(bi)), "ileqg_stage")
+        self._staged = (spec.n, spec.m, spec.N, bi.P * bi.K)
+
+    def run(self, reps=1):
+        """`reps` back-to-back launches of the solve kernel; returns the CUDA-event time in ms
+        (events recorded on the library's own stream)."""
+        ms = C.c_float(0.0)
+        self._check(self.f_run(self.ctx, int(reps), C.byref(ms)), "ileqg_run")
+        return float(ms.value)
+
+    def fetch(self, want=()):
+        n, m, N, B = self._staged
+        res = dict(value=np.empty(B), status=np.empty(B, np.int32), iters=np.empty(B, np.int32),
+                   trials=np.empty(B, np.int32), restarts=np.empty(B, np.int32), mu=np.empty(B),
+                   d_current=np.empty(B))
+        if "x" in want:
+            res["x"] = np.zeros((n, N + 1, B), order="F")
+        if "l" in want:
+            res["l"] = np.zeros((m, N, B), order="F")
+        if "L" in want:
+            res["L"] = np.zeros((m, n, N, B), order="F")
+        out = IleqgOut(_dp(res.get("x")), _dp(res.get("l")), _dp(res.get("L")), _dp(res["value"]),
+                       _ip(res["status"]), _ip(res["iters"]), _ip(res["trials"]), _ip(res["restarts"]),
+                       _dp(res["mu"]), _dp(res["d_current"]), None, 0)
+        self._check(self.f_fetch(self.ctx, C.byref(out)), "ileqg_fetch")
+        return res
+
+    def fp64_probe(self):
+        """measured non-tensor FP64 FMA throughput of this device in TFLOP/s"""
+        tf, ms = C.c_double(0.0), C.c_float(0.0)
+        self._check(self.f_probe(self.ctx, C.byref(tf), C.byref(ms)), "fp64_peak_probe")
+        return float(tf.value)
+
+    def launch_count(self):
+        return int(self.f_launches(self.ctx))
 
     def ce_costs(self, spec, x0, u_init, theta, kl_bound, opts=None, P=None):
         """compute_cost (cross_entropy_bilevel_optimization.jl:173-195)."""

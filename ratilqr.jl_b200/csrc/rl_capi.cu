@@ -1,0 +1,613 @@
+// rl_capi.cu -- the C ABI of libratilqr_b200.so (include/ratilqr.h): context, staging of host
+// arrays into the device SoA workspace, kernel launches on the ctx stream, result download.
+// There is no CPU compute path in this file: every entry point ends in a kernel launch.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rl_host.hpp"
+#include "rl_launch.hpp"
+
+namespace {
+
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct ratilqr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // staged solve
+  bool staged = false;
+  int model_id = 0, cost_id = 0, n = 0, m = 0, N = 0, B = 0, eps_cap = 0;
+  rl::SolveParams sp;
+  DBuf d_cp, d_W, d_Winv, d_detW, d_x0, d_u, d_theta, d_X, d_U, d_Lg, d_DL;
+  DBuf d_value, d_status, d_iters, d_trials, d_restarts, d_mu, d_d, d_cur, d_eps;
+  DBuf d_out1, d_out2, d_out3;  // host-layout staging for x, l, L
+  // scratch for component calls
+  DBuf s[16];
+  DBuf d_cost;
+};
+
+#define CU(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                     \
+      return -100 - (int)e__;                                                             \
+    }                                                                                     \
+  } while (0)
+
+#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+
+static int upload(ratilqr_ctx* ctx, DBuf& b, const void* src, size_t bytes) {
+  CU(b.reserve(bytes ? bytes : 8));
+  if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+#define UP(buf, src, bytes) do { int rc__ = upload(ctx, buf, src, bytes); if (rc__) return rc__; } while (0)
+
+static int check_launch(ratilqr_ctx* ctx, const char* what, int nlaunch = 1) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); return -100 - (int)e; }
+  ctx->launches += nlaunch;
+  return 0;
+}
+
+static const char* check_opts(const ratilqr_ileqg_opts* o) {  // the @asserts of ileqg.jl:195-201
+  if (!o) return "null opts";
+  if (!(o->lambda > 0 && o->lambda < 1)) return "lambda has to be in (0, 1)";
+  if (!(o->d > 0)) return "d > 0 is necessary";
+  if (!(o->mu_min > 0)) return "mu_min > 0 is necessary";
+  if (!(o->delta_0 > 0)) return "delta_0 > 0 is necessary";
+  if (!(o->eps_init > 0 && o->eps_init <= 1)) return "eps_init has to be in (0, 1]";
+  if (!(o->eps_init > o->eps_min)) return "eps_init > eps_min is necessary";
+  if (!(o->eps_min > 0 && o->eps_min < 1)) return "eps_min has to be in (0, 1)";
+  if (o->iter_max < 1) return "iter_max must be >= 1";
+  return nullptr;
+}
+
+__global__ void k_ce_cost(int B, const double* value, const int32_t* status, const double* theta, double kl, double* cost) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  // cost = value + kl_bound/theta (cross_entropy_bilevel_optimization.jl:193); any exception => Inf (:161-165)
+  cost[b] = status[b] == 0 ? value[b] + kl / theta[b] : HUGE_VAL;
+}
+
+static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                          const ratilqr_batch_in* in, int eps_cap) {
+  ctx->staged = false;
+  if (const char* m = rlh::check_desc(desc, true)) FAIL(-1, m);
+  if (const char* m = check_opts(opts)) FAIL(-3, m);
+  if (!in || in->P < 1 || in->K < 1 || !in->x0 || !in->u_init || !in->theta) FAIL(-1, "bad batch description");
+  if ((in->x0_count != 1 && in->x0_count != in->P) || (in->u_count != 1 && in->u_count != in->P)) FAIL(-1, "x0_count/u_count must be 1 or P");
+  if (desc->cost_params_count != 1 && desc->cost_params_count != in->P) FAIL(-1, "cost_params_count must be 1 or P");
+  CU(cudaSetDevice(ctx->device));
+  const int n = desc->n, m = desc->m, N = desc->N;
+  const size_t B = (size_t)in->P * in->K;
+  if (B > 0x7fffffffull) FAIL(-1, "batch too large");
+  rlh::WPrep wp;
+  if (!rlh::prep_W(n, N, desc->W, desc->W_time_varying, wp)) FAIL(-2, "W(k) is not positive definite (inv(W) / MvNormal need PD)");
+  UP(ctx->d_W, wp.W.data(), wp.W.size() * 8);
+  UP(ctx->d_Winv, wp.Winv.data(), wp.Winv.size() * 8);
+  UP(ctx->d_detW, wp.detW.data(), wp.detW.size() * 8);
+  UP(ctx->d_cp, desc->cost_params, (size_t)desc->n_cost_params * desc->cost_params_count * 8);
+  UP(ctx->d_x0, in->x0, (size_t)n * in->x0_count * 8);
+  UP(ctx->d_u, in->u_init, (size_t)m * N * in->u_count * 8);
+  UP(ctx->d_theta, in->theta, B * 8);
+  CU(ctx->d_X.reserve(2 * (size_t)(N + 1) * n * B * 8));
+  CU(ctx->d_U.reserve(2 * (size_t)N * m * B * 8));
+  CU(ctx->d_Lg.reserve((size_t)N * m * n * B * 8));
+  CU(ctx->d_DL.reserve((size_t)N * m * B * 8));
+  CU(ctx->d_value.reserve(B * 8));
+  CU(ctx->d_mu.reserve(B * 8));
+  CU(ctx->d_d.reserve(B * 8));
+  CU(ctx->d_status.reserve(B * 4));
+  CU(ctx->d_iters.reserve(B * 4));
+  CU(ctx->d_trials.reserve(B * 4));
+  CU(ctx->d_restarts.reserve(B * 4));
+  CU(ctx->d_cur.reserve(B * 4));
+  if (eps_cap > 0) {
+    CU(ctx->d_eps.reserve(B * eps_cap * 16));
+    CU(cudaMemsetAsync(ctx->d_eps.p, 0, B * eps_cap * 16, ctx->stream));
+  }
+  // gains of instances that fail before their first optimising pass stay zero (initialize!: L = 0)
+  CU(cudaMemsetAsync(ctx->d_Lg.p, 0, (size_t)N * m * n * B * 8, ctx->stream));
+  rl::SolveParams& P = ctx->sp;
+  memset(&P, 0, sizeof(P));
+  P.N = N; P.B = (int)B; P.K = in->K;
+  for (int i = 0; i < 8; ++i) P.mp[i] = i < desc->n_model_params ? desc->model_params[i] : 0.0;
+  P.cost_params = ctx->d_cp.as<double>(); P.ncp = desc->n_cost_params; P.cp_count = desc->cost_params_count;
+  P.W = ctx->d_W.as<double>(); P.Winv = ctx->d_Winv.as<double>(); P.detW = ctx->d_detW.as<double>(); P.W_tv = desc->W_time_varying;
+  P.x0 = ctx->d_x0.as<double>(); P.x0_count = in->x0_count;
+  P.u_init = ctx->d_u.as<double>(); P.u_count = in->u_count;
+  P.theta = ctx->d_theta.as<double>();
+  P.mu_min = opts->mu_min; P.delta_0 = opts->delta_0; P.lambda = opts->lambda; P.d = opts->d;
+  P.iter_max = opts->iter_max; P.eps_auto = opts->adaptive_eps_init; P.eps_init = opts->eps_init; P.eps_min = opts->eps_min;
+  P.X = ctx->d_X.as<double>(); P.U = ctx->d_U.as<double>(); P.Lg = ctx->d_Lg.as<double>(); P.DL = ctx->d_DL.as<double>();
+  P.value = ctx->d_value.as<double>(); P.status = ctx->d_status.as<int32_t>(); P.iters = ctx->d_iters.as<int32_t>();
+  P.trials = ctx->d_trials.as<int32_t>(); P.restarts = ctx->d_restarts.as<int32_t>();
+  P.mu_out = ctx->d_mu.as<double>(); P.d_out = ctx->d_d.as<double>(); P.cur = ctx->d_cur.as<int32_t>();
+  P.eps_hist = eps_cap > 0 ? ctx->d_eps.as<double>() : nullptr; P.eps_hist_cap = eps_cap;
+  ctx->model_id = desc->model_id; ctx->cost_id = desc->cost_id;
+  ctx->n = n; ctx->m = m; ctx->N = N; ctx->B = (int)B; ctx->eps_cap = eps_cap;
+  ctx->staged = true;
+  return 0;
+}
+
+static int run_internal(ratilqr_ctx* ctx, int reps, float* ms_total) {
+  if (!ctx->staged) FAIL(-4, "nothing staged: call ratilqr_ileqg_stage first");
+  if (reps < 1) reps = 1;
+  CU(cudaSetDevice(ctx->device));
+  if (ms_total) CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int r = 0; r < reps; ++r) {
+    if (rll::launch_solve(ctx->model_id, ctx->cost_id, ctx->sp, ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
+    if (int rc = check_launch(ctx, "k_ileqg_solve")) return rc;
+  }
+  if (ms_total) {
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(ms_total, ctx->ev0, ctx->ev1));
+  }
+  return 0;
+}
+
+static int fetch_internal(ratilqr_ctx* ctx, ratilqr_ileqg_out* out) {
+  if (!ctx->staged) FAIL(-4, "nothing staged");
+  if (!out) FAIL(-1, "null out");
+  CU(cudaSetDevice(ctx->device));
+  const int n = ctx->n, m = ctx->m, N = ctx->N;
+  const size_t B = (size_t)ctx->B;
+  cudaStream_t st = ctx->stream;
+  double *dx = nullptr, *dl = nullptr, *dL = nullptr;
+  if (out->x) { CU(ctx->d_out1.reserve((size_t)n * (N + 1) * B * 8)); dx = ctx->d_out1.as<double>(); }
+  if (out->l) { CU(ctx->d_out2.reserve((size_t)m * N * B * 8)); dl = ctx->d_out2.as<double>(); }
+  if (out->L) { CU(ctx->d_out3.reserve((size_t)m * n * N * B * 8)); dL = ctx->d_out3.as<double>(); }
+  if (dx || dl || dL) {
+    rll::launch_gather(n, m, N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.cur, dx, dl, dL, st);
+    if (int rc = check_launch(ctx, "k_gather", (dx ? 1 : 0) + (dl ? 1 : 0) + (dL ? 1 : 0))) return rc;
+  }
+#define DOWN(dst, src, bytes) if (dst) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))
+  DOWN(out->x, dx, (size_t)n * (N + 1) * B * 8);
+  DOWN(out->l, dl, (size_t)m * N * B * 8);
+  DOWN(out->L, dL, (size_t)m * n * N * B * 8);
+  DOWN(out->value, ctx->sp.value, B * 8);
+  DOWN(out->status, ctx->sp.status, B * 4);
+  DOWN(out->iters, ctx->sp.iters, B * 4);
+  DOWN(out->trials, ctx->sp.trials, B * 4);
+  DOWN(out->restarts, ctx->sp.restarts, B * 4);
+  DOWN(out->mu, ctx->sp.mu_out, B * 8);
+  DOWN(out->d_current, ctx->sp.d_out, B * 8);
+  if (out->eps_hist && out->eps_hist_cap > 0) {
+    if (out->eps_hist_cap != ctx->eps_cap) FAIL(-1, "eps_hist_cap differs from the staged capacity");
+    DOWN(out->eps_hist, ctx->sp.eps_hist, B * ctx->eps_cap * 16);
+  }
+#undef DOWN
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" {
+
+int32_t ratilqr_version(void) { return 100; }
+
+int32_t ratilqr_model_dims(int32_t model_id, int32_t* n, int32_t* m, int32_t* n_params) {
+  int a, b, c;
+  if (!rlh::model_dims(model_id, &a, &b, &c)) return -1;
+  if (n) *n = a;
+  if (m) *m = b;
+  if (n_params) *n_params = c;
+  return 0;
+}
+
+int32_t ratilqr_cost_param_count(int32_t cost_id, int32_t n, int32_t m) { return rlh::cost_param_count(cost_id, n, m); }
+
+int32_t ratilqr_create(ratilqr_ctx** out, int32_t device_id) {
+  if (!out) return -1;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count < 1) return -10;  // no CUDA device: there is no CPU fallback
+  if (device_id < 0 || device_id >= count) return -11;
+  ratilqr_ctx* ctx = new ratilqr_ctx();
+  ctx->device = device_id;
+  if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    delete ctx;
+    return -12;
+  }
+  *out = ctx;
+  return 0;
+}
+
+int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DBuf* all[] = {&ctx->d_cp, &ctx->d_W, &ctx->d_Winv, &ctx->d_detW, &ctx->d_x0, &ctx->d_u, &ctx->d_theta, &ctx->d_X,
+                 &ctx->d_U, &ctx->d_Lg, &ctx->d_DL, &ctx->d_value, &ctx->d_status, &ctx->d_iters, &ctx->d_trials,
+                 &ctx->d_restarts, &ctx->d_mu, &ctx->d_d, &ctx->d_cur, &ctx->d_eps, &ctx->d_out1, &ctx->d_out2,
+                 &ctx->d_out3, &ctx->d_cost};
+  for (DBuf* b : all) b->release();
+  for (DBuf& b : ctx->s) b.release();
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+const char* ratilqr_last_error(const ratilqr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+int64_t ratilqr_launch_count(const ratilqr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t ratilqr_ileqg_stage(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                            const ratilqr_batch_in* in) {
+  if (!ctx) return -1;
+  int rc = stage_internal(ctx, desc, opts, in, 0);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t ratilqr_ileqg_run(ratilqr_ctx* ctx, int32_t reps, float* ms_total) {
+  if (!ctx) return -1;
+  int rc = run_internal(ctx, reps, ms_total);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t ratilqr_ileqg_fetch(ratilqr_ctx* ctx, ratilqr_ileqg_out* out) {
+  if (!ctx) return -1;
+  return fetch_internal(ctx, out);
+}
+
+int32_t ratilqr_ileqg_solve_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                                  const ratilqr_batch_in* in, ratilqr_ileqg_out* out) {
+  if (!ctx) return -1;
+  if (!out) FAIL(-1, "null out");
+  int rc = stage_internal(ctx, desc, opts, in, out->eps_hist ? out->eps_hist_cap : 0);
+  if (rc) return rc;
+  rc = run_internal(ctx, 1, nullptr);
+  if (rc) return rc;
+  return fetch_internal(ctx, out);
+}
+
+int32_t ratilqr_ce_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                         const ratilqr_batch_in* in, double kl_bound, double* cost, int32_t* status) {
+  if (!ctx) return -1;
+  if (!cost) FAIL(-1, "null cost");
+  int rc = stage_internal(ctx, desc, opts, in, 0);
+  if (rc) return rc;
+  rc = run_internal(ctx, 1, nullptr);
+  if (rc) return rc;
+  const int B = ctx->B;
+  CU(ctx->d_cost.reserve((size_t)B * 8));
+  k_ce_cost<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, ctx->sp.value, ctx->sp.status, ctx->sp.theta, kl_bound, ctx->d_cost.as<double>());
+  if ((rc = check_launch(ctx, "k_ce_cost"))) return rc;
+  CU(cudaMemcpyAsync(cost, ctx->d_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CU(cudaMemcpyAsync(status, ctx->sp.status, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- component entry points ---------------------------------------------------------------------
+static int fill_comp(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int B, rll::CompArgs& a, bool differentiable) {
+  ctx->staged = false;  // shares d_cp / d_W with a staged solve
+  if (const char* m = rlh::check_desc(desc, differentiable)) FAIL(-1, m);
+  if (B < 1) FAIL(-1, "B must be >= 1");
+  CU(cudaSetDevice(ctx->device));
+  memset(&a, 0, sizeof(a));
+  a.model_id = desc->model_id; a.cost_id = desc->cost_id; a.n = desc->n; a.m = desc->m; a.N = desc->N; a.B = B;
+  for (int i = 0; i < 8; ++i) a.mp[i] = i < desc->n_model_params ? desc->model_params[i] : 0.0;
+  UP(ctx->d_cp, desc->cost_params, (size_t)desc->n_cost_params * 8);
+  a.cp = ctx->d_cp.as<double>();
+  return 0;
+}
+
+#define DOWNSYNC(dst, src, bytes) do { if (dst) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); } while (0)
+
+int32_t ratilqr_rollout_open_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t B, const double* x0,
+                                   const double* u, double* x, int32_t* status) {
+  if (!ctx) return -1;
+  rll::CompArgs a;
+  if (int rc = fill_comp(ctx, desc, B, a, false)) return rc;
+  const size_t n = a.n, m = a.m, N = a.N;
+  UP(ctx->s[0], x0, n * B * 8); UP(ctx->s[1], u, m * N * B * 8);
+  CU(ctx->s[2].reserve(n * (N + 1) * B * 8)); CU(ctx->s[3].reserve((size_t)B * 4));
+  CU(cudaMemsetAsync(ctx->s[2].p, 0, n * (N + 1) * B * 8, ctx->stream));
+  a.x0 = ctx->s[0].as<double>(); a.u = ctx->s[1].as<double>(); a.x = ctx->s[2].as<double>(); a.status = ctx->s[3].as<int32_t>();
+  if (rll::launch_rollout_open(a, ctx->stream)) FAIL(-5, "model not compiled in");
+  if (int rc = check_launch(ctx, "k_rollout_open")) return rc;
+  DOWNSYNC(x, a.x, n * (N + 1) * B * 8); DOWNSYNC(status, a.status, (size_t)B * 4);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t ratilqr_rollout_closed_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t B, const double* xbar,
+                                     const double* l, const double* L, double* x_new, double* u_new, int32_t* status) {
+  if (!ctx) return -1;
+  rll::CompArgs a;
+  if (int rc = fill_comp(ctx, desc, B, a, false)) return rc;
+  const size_t n = a.n, m = a.m, N = a.N;
+  UP(ctx->s[0], xbar, n * (N + 1) * B * 8); UP(ctx->s[1], l, m * N * B * 8); UP(ctx->s[2], L, m * n * N * B * 8);
+  CU(ctx->s[3].reserve(n * (N + 1) * B * 8)); CU(ctx->s[4].reserve(m * N * B * 8)); CU(ctx->s[5].reserve((size_t)B * 4));
+  a.xbar = ctx->s[0].as<double>(); a.l = ctx->s[1].as<double>(); a.L = ctx->s[2].as<double>();
+  a.x = ctx->s[3].as<double>(); a.u_new = ctx->s[4].as<double>(); a.status = ctx->s[5].as<int32_t>();
+  if (rll::launch_rollout_closed(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  if (int rc = check_launch(ctx, "k_rollout_closed")) return rc;
+  DOWNSYNC(x_new, a.x, n * (N + 1) * B * 8); DOWNSYNC(u_new, a.u_new, m * N * B * 8); DOWNSYNC(status, a.status, (size_t)B * 4);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t ratilqr_integrate_cost_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t B, const double* x,
+                                     const double* u, double* cost, int32_t* status) {
+  if (!ctx) return -1;
+  rll::CompArgs a;
+  if (int rc = fill_comp(ctx, desc, B, a, false)) return rc;
+  const size_t n = a.n, m = a.m, N = a.N;
+  UP(ctx->s[0], x, n * (N + 1) * B * 8); UP(ctx->s[1], u, m * N * B * 8);
+  CU(ctx->s[2].reserve((size_t)B * 8)); CU(ctx->s[3].reserve((size_t)B * 4));
+  a.x = ctx->s[0].as<double>(); a.u = ctx->s[1].as<double>(); a.cost = ctx->s[2].as<double>(); a.status = ctx->s[3].as<int32_t>();
+  if (rll::launch_integrate_cost(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  if (int rc = check_launch(ctx, "k_integrate_cost")) return rc;
+  DOWNSYNC(cost, a.cost, (size_t)B * 8); DOWNSYNC(status, a.status, (size_t)B * 4);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t ratilqr_linearize_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t B, const double* x,
+                                const double* u, double* q, double* qv, double* Q, double* r, double* R, double* Pm,
+                                double* A, double* Bm, int32_t* status) {
+  if (!ctx) return -1;
+  rll::CompArgs a;
+  if (int rc = fill_comp(ctx, desc, B, a, true)) return rc;
+  const size_t n = a.n, m = a.m, N = a.N;
+  const size_t sz[8] = {(N + 1) * B, n * (N + 1) * B, n * n * (N + 1) * B, m * N * B, m * m * N * B, m * n * N * B, n * n * N * B, n * m * N * B};
+  UP(ctx->s[0], x, n * (N + 1) * B * 8); UP(ctx->s[1], u, m * N * B * 8);
+  for (int i = 0; i < 8; ++i) CU(ctx->s[2 + i].reserve(sz[i] * 8));
+  CU(ctx->s[10].reserve((size_t)B * 4));
+  CU(cudaMemsetAsync(ctx->s[10].p, 0, (size_t)B * 4, ctx->stream));
+  a.x = ctx->s[0].as<double>(); a.u = ctx->s[1].as<double>();
+  a.q = ctx->s[2].as<double>(); a.qv = ctx->s[3].as<double>(); a.Q = ctx->s[4].as<double>(); a.r = ctx->s[5].as<double>();
+  a.R = ctx->s[6].as<double>(); a.Pm = ctx->s[7].as<double>(); a.A = ctx->s[8].as<double>(); a.Bm = ctx->s[9].as<double>();
+  a.status = ctx->s[10].as<int32_t>();
+  if (rll::launch_linearize(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  if (int rc = check_launch(ctx, "k_linearize")) return rc;
+  double* outs[8] = {q, qv, Q, r, R, Pm, A, Bm};
+  for (int i = 0; i < 8; ++i) DOWNSYNC(outs[i], ctx->s[2 + i].p, sz[i] * 8);
+  DOWNSYNC(status, a.status, (size_t)B * 4);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t ratilqr_riccati_batch(ratilqr_ctx* ctx, int32_t n_, int32_t m_, int32_t N_, int32_t B, int32_t optimise,
+                              const double* q, const double* qv, const double* Q, const double* r, const double* R,
+                              const double* Pm, const double* A, const double* Bm, const double* W, const double* theta,
+                              double mu_min, double delta_0, double* mu, double* delta, double* L, double* dl,
+                              double* s, double* sv, double* S, int32_t* status, int32_t* restarts) {
+  if (!ctx) return -1;
+  if (B < 1 || N_ < 1 || !q || !qv || !Q || !r || !R || !Pm || !A || !Bm || !W || !theta || !mu || !delta || !L || !s || !sv || !S)
+    FAIL(-1, "null argument");
+  if (optimise && !dl) FAIL(-1, "dl output required when optimising");
+  ctx->staged = false;
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = n_, m = m_, N = N_;
+  rlh::WPrep wp;
+  if (!rlh::prep_W(n_, N_, W, 0, wp)) FAIL(-2, "W is not positive definite");
+  const size_t sz[8] = {(N + 1) * B, n * (N + 1) * B, n * n * (N + 1) * B, m * N * B, m * m * N * B, m * n * N * B, n * n * N * B, n * m * N * B};
+  const double* ins[8] = {q, qv, Q, r, R, Pm, A, Bm};
+  for (int i = 0; i < 8; ++i) UP(ctx->s[i], ins[i], sz[i] * 8);
+  UP(ctx->d_W, wp.W.data(), n * n * 8); UP(ctx->d_Winv, wp.Winv.data(), n * n * 8);
+  UP(ctx->s[8], theta, (size_t)B * 8); UP(ctx->s[9], mu, (size_t)B * 8); UP(ctx->s[10], delta, (size_t)B * 8);
+  if (optimise) { CU(ctx->s[11].reserve(m * n * N * B * 8)); CU(ctx->s[12].reserve(m * N * B * 8)); }
+  else { UP(ctx->s[11], L, m * n * N * B * 8); if (dl) UP(ctx->s[12], dl, m * N * B * 8); }
+  CU(ctx->s[13].reserve(sz[0] * 8)); CU(ctx->s[14].reserve(sz[1] * 8)); CU(ctx->s[15].reserve(sz[2] * 8));
+  CU(ctx->d_status.reserve((size_t)B * 4)); CU(ctx->d_restarts.reserve((size_t)B * 4));
+  rll::RiccatiArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n_; a.m = m_; a.N = N_; a.B = B; a.optimise = optimise;
+  a.q = ctx->s[0].as<double>(); a.qv = ctx->s[1].as<double>(); a.Q = ctx->s[2].as<double>(); a.r = ctx->s[3].as<double>();
+  a.R = ctx->s[4].as<double>(); a.Pm = ctx->s[5].as<double>(); a.A = ctx->s[6].as<double>(); a.Bm = ctx->s[7].as<double>();
+  a.W = ctx->d_W.as<double>(); a.Winv = ctx->d_Winv.as<double>(); a.detW = wp.detW[0];
+  a.theta = ctx->s[8].as<double>(); a.mu_min = mu_min; a.delta_0 = delta_0;
+  a.mu = ctx->s[9].as<double>(); a.delta = ctx->s[10].as<double>(); a.L = ctx->s[11].as<double>(); a.dl = ctx->s[12].as<double>();
+  a.has_dl = dl != nullptr;
+  a.s = ctx->s[13].as<double>(); a.sv = ctx->s[14].as<double>(); a.S = ctx->s[15].as<double>();
+  a.status = ctx->d_status.as<int32_t>(); a.restarts = ctx->d_restarts.as<int32_t>();
+  if (rll::launch_riccati(a, ctx->stream)) FAIL(-5, "(n, m) not compiled in");
+  if (int rc = check_launch(ctx, "k_riccati")) return rc;
+  DOWNSYNC(s, a.s, sz[0] * 8); DOWNSYNC(sv, a.sv, sz[1] * 8); DOWNSYNC(S, a.S, sz[2] * 8);
+  DOWNSYNC(mu, a.mu, (size_t)B * 8); DOWNSYNC(delta, a.delta, (size_t)B * 8);
+  if (optimise) { DOWNSYNC(L, a.L, m * n * N * B * 8); DOWNSYNC(dl, a.dl, m * N * B * 8); }
+  DOWNSYNC(status, a.status, (size_t)B * 4); DOWNSYNC(restarts, a.restarts, (size_t)B * 4);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t P, const double* xbar,
+                           const double* l, const double* L, int32_t n_samples, const double* noise, uint64_t seed,
+                           double theta_risk, double* J, double* stats, double* x_out) {
+  if (!ctx) return -1;
+  if (const char* msg = rlh::check_desc(desc, false)) FAIL(-1, msg);
+  if (P < 1 || n_samples < 1 || !xbar || !l || !L) FAIL(-1, "bad arguments");
+  if (desc->cost_params_count != 1 && desc->cost_params_count != P) FAIL(-1, "cost_params_count must be 1 or P");
+  ctx->staged = false;
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = desc->n, m = desc->m, N = desc->N, S = (size_t)n_samples * P;
+  rlh::WPrep wp;
+  if (!rlh::prep_W(desc->n, desc->N, desc->W, desc->W_time_varying, wp)) FAIL(-2, "W(k) is not positive definite");
+  rll::McArgs a;
+  memset(&a, 0, sizeof(a));
+  a.model_id = desc->model_id; a.cost_id = desc->cost_id; a.N = desc->N; a.P = P; a.n_samples = n_samples;
+  for (int i = 0; i < 8; ++i) a.mp[i] = i < desc->n_model_params ? desc->model_params[i] : 0.0;
+  UP(ctx->d_cp, desc->cost_params, (size_t)desc->n_cost_params * desc->cost_params_count * 8);
+  a.cp = ctx->d_cp.as<double>(); a.ncp = desc->n_cost_params; a.cp_count = desc->cost_params_count;
+  UP(ctx->s[0], xbar, n * (N + 1) * P * 8); UP(ctx->s[1], l, m * N * P * 8); UP(ctx->s[2], L, m * n * N * P * 8);
+  a.xbar = ctx->s[0].as<double>(); a.l = ctx->s[1].as<double>(); a.L = ctx->s[2].as<double>();
+  if (noise) { UP(ctx->s[3], noise, n * N * S * 8); a.noise = ctx->s[3].as<double>(); }
+  UP(ctx->s[4], wp.cholW.data(), wp.cholW.size() * 8);
+  a.cholW = ctx->s[4].as<double>(); a.W_tv = desc->W_time_varying; a.seed = seed;
+  CU(ctx->s[5].reserve(S * 8)); a.J = ctx->s[5].as<double>();
+  if (x_out) { CU(ctx->s[6].reserve(n * (N + 1) * S * 8)); a.x_out = ctx->s[6].as<double>(); }
+  if (rll::launch_mc_rollout(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  if (int rc = check_launch(ctx, "k_mc_rollout")) return rc;
+  if (stats) {
+    CU(ctx->s[7].reserve((size_t)P * 24));
+    rll::launch_mc_stats(a.J, n_samples, P, theta_risk, ctx->s[7].as<double>(), ctx->stream);
+    if (int rc = check_launch(ctx, "k_mc_stats")) return rc;
+    DOWNSYNC(stats, ctx->s[7].p, (size_t)P * 24);
+  }
+  DOWNSYNC(J, a.J, S * 8);
+  DOWNSYNC(x_out, a.x_out, n * (N + 1) * S * 8);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static int pets_fill(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_generative_desc* gen,
+                     const double* x0, int C, int particles, rll::PetsArgs& a) {
+  if (const char* msg = rlh::check_desc(desc, false)) FAIL(-1, msg);
+  if (C < 1 || particles < 1 || !x0) FAIL(-1, "bad arguments");
+  ctx->staged = false;
+  CU(cudaSetDevice(ctx->device));
+  rlh::WPrep wp;
+  if (!rlh::prep_W(desc->n, desc->N, desc->W, 0, wp)) FAIL(-2, "W is not positive definite");
+  memset(&a, 0, sizeof(a));
+  a.model_id = desc->model_id; a.cost_id = desc->cost_id; a.N = desc->N; a.C = C; a.particles = particles;
+  for (int i = 0; i < 8; ++i) a.mp[i] = i < desc->n_model_params ? desc->model_params[i] : 0.0;
+  a.n_mp = desc->n_model_params;
+  a.noise_kind = gen ? gen->noise_kind : 0;
+  a.noise_scale = gen ? gen->noise_scale : 1.0;
+  a.n_ens = gen && gen->n_ensemble > 1 ? gen->n_ensemble : 1;
+  if (gen && gen->ensemble_params && a.n_ens > 1) {
+    UP(ctx->s[8], gen->ensemble_params, (size_t)a.n_ens * desc->n_model_params * 8);
+    a.ens_params = ctx->s[8].as<double>();
+  }
+  UP(ctx->d_cp, desc->cost_params, (size_t)desc->n_cost_params * 8);
+  a.cp = ctx->d_cp.as<double>();
+  UP(ctx->s[9], x0, (size_t)desc->n * 8);
+  a.x0 = ctx->s[9].as<double>();
+  UP(ctx->s[10], wp.cholW.data(), wp.cholW.size() * 8);
+  a.cholW = ctx->s[10].as<double>();
+  return 0;
+}
+
+int32_t ratilqr_pets_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_generative_desc* gen,
+                           const double* x0, const double* controls, int32_t C, int32_t particles, const double* noise,
+                           uint64_t seed, double* cost) {
+  if (!ctx) return -1;
+  if (!controls || !cost) FAIL(-1, "null argument");
+  rll::PetsArgs a;
+  if (int rc = pets_fill(ctx, desc, gen, x0, C, particles, a)) return rc;
+  const size_t n = desc->n, m = desc->m, N = desc->N;
+  UP(ctx->s[0], controls, m * N * C * 8);
+  a.controls = ctx->s[0].as<double>();
+  if (noise) { UP(ctx->s[1], noise, n * N * (size_t)particles * C * 8); a.noise = ctx->s[1].as<double>(); }
+  a.seed = seed; a.stream_offset = 0;
+  CU(ctx->s[2].reserve((size_t)C * 8));
+  a.cost = ctx->s[2].as<double>();
+  if (rll::launch_pets_costs(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  if (int rc = check_launch(ctx, "k_pets_costs")) return rc;
+  DOWNSYNC(cost, a.cost, (size_t)C * 8);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t ratilqr_pets_refit(ratilqr_ctx* ctx, int32_t m_, int32_t N_, int32_t C, int32_t num_elite, double smoothing,
+                           const double* controls, const double* cost, double* mu, double* Sigma, int32_t* elite_idx) {
+  if (!ctx) return -1;
+  if (!controls || !cost || !mu || !Sigma || num_elite < 1 || num_elite > C) FAIL(-1, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const size_t m = m_, N = N_;
+  UP(ctx->s[0], controls, m * N * C * 8); UP(ctx->s[2], cost, (size_t)C * 8);
+  UP(ctx->s[3], mu, m * N * 8); UP(ctx->s[4], Sigma, m * m * N * 8);
+  CU(ctx->s[5].reserve((size_t)num_elite * 4));
+  rll::launch_pets_refit(m_, N_, C, num_elite, smoothing, ctx->s[0].as<double>(), ctx->s[2].as<double>(),
+                         ctx->s[3].as<double>(), ctx->s[4].as<double>(), ctx->s[5].as<int32_t>(), nullptr, ctx->stream);
+  if (int rc = check_launch(ctx, "k_pets_refit", 2)) return rc;
+  DOWNSYNC(mu, ctx->s[3].p, m * N * 8); DOWNSYNC(Sigma, ctx->s[4].p, m * m * N * 8);
+  DOWNSYNC(elite_idx, ctx->s[5].p, (size_t)num_elite * 4);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t ratilqr_pets_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_generative_desc* gen,
+                           const double* x0, int32_t C, int32_t particles, int32_t num_elite, int32_t iter_max,
+                           double smoothing, const double* z_inject, const double* noise, uint64_t seed, double* mu,
+                           double* Sigma) {
+  if (!ctx) return -1;
+  if (!mu || !Sigma || num_elite < 2 || num_elite > C || iter_max < 0) FAIL(-1, "bad arguments");
+  rll::PetsArgs a;
+  if (int rc = pets_fill(ctx, desc, gen, x0, C, particles, a)) return rc;
+  const size_t n = desc->n, m = desc->m, N = desc->N;
+  const size_t zsz = m * N * C, nsz = n * N * (size_t)particles * C;
+  if (z_inject) UP(ctx->s[1], z_inject, zsz * iter_max * 8);
+  if (noise) UP(ctx->s[11], noise, nsz * iter_max * 8);
+  CU(ctx->s[0].reserve(zsz * 8)); CU(ctx->s[2].reserve((size_t)C * 8));
+  UP(ctx->s[3], mu, m * N * 8); UP(ctx->s[4], Sigma, m * m * N * 8);
+  CU(ctx->s[5].reserve((size_t)num_elite * 4)); CU(ctx->s[6].reserve(4));
+  CU(cudaMemsetAsync(ctx->s[6].p, 0, 4, ctx->stream));
+  a.controls = ctx->s[0].as<double>(); a.cost = ctx->s[2].as<double>(); a.seed = seed;
+  for (int it = 0; it < iter_max; ++it) {  // step! pets.jl:193-245, all on the device
+    rll::launch_pets_sample(desc->m, desc->N, C, ctx->s[3].as<double>(), ctx->s[4].as<double>(),
+                            z_inject ? ctx->s[1].as<double>() + zsz * it : nullptr, seed ^ 0x5bd1e995u,
+                            (uint64_t)it * (uint64_t)C, ctx->s[0].as<double>(), ctx->s[6].as<int32_t>(), ctx->stream);
+    a.noise = noise ? ctx->s[11].as<double>() + nsz * it : nullptr;
+    a.stream_offset = (uint64_t)it * (uint64_t)C * (uint64_t)particles;
+    if (rll::launch_pets_costs(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+    rll::launch_pets_refit(desc->m, desc->N, C, num_elite, smoothing, a.controls, a.cost, ctx->s[3].as<double>(),
+                           ctx->s[4].as<double>(), ctx->s[5].as<int32_t>(), nullptr, ctx->stream);
+    if (int rc = check_launch(ctx, "pets step", 4)) return rc;
+  }
+  int32_t err = 0;
+  CU(cudaMemcpyAsync(&err, ctx->s[6].p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DOWNSYNC(mu, ctx->s[3].p, m * N * 8); DOWNSYNC(Sigma, ctx->s[4].p, m * m * N * 8);
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (err) FAIL(-4, "a Sigma_t is not positive definite (PosDefException in MvNormal, pets.jl:212)");
+  return 0;
+}
+
+int32_t ratilqr_fp64_peak_probe(ratilqr_ctx* ctx, double* tflops, float* ms) {
+  if (!ctx) return -1;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->s[0].reserve(64));
+  const int iters = 1 << 16;
+  rll::launch_fp64_probe(ctx->s[0].as<double>(), 1 << 10, ctx->stream);  // warm-up
+  float best = 1e30f;
+  double flops = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    flops = rll::launch_fp64_probe(ctx->s[0].as<double>(), iters, ctx->stream);
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev1));
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+    if (t < best) best = t;
+  }
+  if (int rc = check_launch(ctx, "k_fp64_probe", 4)) return rc;
+  if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms) *ms = best;
+  return 0;
+}
+
+}  // extern "C"

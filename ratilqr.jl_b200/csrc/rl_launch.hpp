@@ -1,0 +1,84 @@
+// rl_launch.hpp -- launchers implemented in the rl_kernels_*.cu translation units.
+// All pointers are DEVICE pointers.  Every launcher returns 0, or -1 if the (model, cost)
+// pair is not compiled in; CUDA errors are checked by the caller (cudaGetLastError).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rl_core.cuh"
+
+namespace rll {
+
+// persistent one-thread-per-instance iLEQG solve (rl_kernels_solve.cu)
+int launch_solve(int model_id, int cost_id, const rl::SolveParams& P, cudaStream_t st);
+
+// SoA workspace -> host-layout outputs (x, l, L), tile transpose through shared memory
+void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg, const int32_t* cur,
+                   double* x_out, double* l_out, double* L_out, cudaStream_t st);
+
+struct CompArgs {
+  int model_id, cost_id, n, m, N, B;
+  double mp[8];
+  const double* cp;  // device, one block
+  // rollouts / cost / linearize (host layout, instance slowest)
+  const double *x0, *u, *xbar, *l, *L;
+  double *x, *u_new, *cost;
+  double *q, *qv, *Q, *r, *R, *Pm, *A, *Bm;
+  int32_t* status;
+};
+int launch_rollout_open(const CompArgs& a, cudaStream_t st);
+int launch_rollout_closed(const CompArgs& a, cudaStream_t st);
+int launch_integrate_cost(const CompArgs& a, cudaStream_t st);
+int launch_linearize(const CompArgs& a, cudaStream_t st);
+
+struct RiccatiArgs {
+  int n, m, N, B, optimise;
+  const double *q, *qv, *Q, *r, *R, *Pm, *A, *Bm, *W, *Winv;
+  double detW;
+  const double* theta;
+  double mu_min, delta_0;
+  double *mu, *delta, *L, *dl, *s, *sv, *S;
+  int has_dl;
+  int32_t *status, *restarts;
+};
+int launch_riccati(const RiccatiArgs& a, cudaStream_t st);
+
+struct McArgs {
+  int model_id, cost_id, N, P, n_samples;
+  double mp[8];
+  const double* cp; int ncp, cp_count;
+  const double *xbar, *l, *L;        // per problem
+  const double* noise;               // n*N*n_samples*P or null
+  const double* cholW; int W_tv;     // n*n [*N]
+  uint64_t seed;
+  double* J; double* x_out;
+};
+int launch_mc_rollout(const McArgs& a, cudaStream_t st);
+// per-problem mean / unbiased variance / entropic risk of J (deterministic single-block reduction)
+void launch_mc_stats(const double* J, int n_samples, int P, double theta_risk, double* stats, cudaStream_t st);
+
+struct PetsArgs {
+  int model_id, cost_id, N, C, particles;
+  double mp[8];
+  const double* ens_params; int n_ens, n_mp;  // device, or null
+  const double* cp;
+  const double* x0;
+  const double* controls;  // m*N*C
+  const double* noise;     // n*N*particles*C or null
+  const double* cholW;
+  int noise_kind; double noise_scale;
+  uint64_t seed; uint64_t stream_offset;
+  double* cost;            // C
+};
+int launch_pets_costs(const PetsArgs& a, cudaStream_t st);
+// u = mu_t + chol_lower(Sigma_t) z ; z injected (m*N*C) or Philox. returns via err[0] != 0 if a Sigma_t is not PD
+void launch_pets_sample(int m, int N, int C, const double* mu, const double* Sigma, const double* z, uint64_t seed,
+                        uint64_t stream_offset, double* controls, int32_t* err, cudaStream_t st);
+// stable top-k elites + smoothed refit (pets.jl:159-191)
+void launch_pets_refit(int m, int N, int C, int num_elite, double smoothing, const double* controls,
+                       const double* cost, double* mu, double* Sigma, int32_t* elite_idx, int32_t* sort_ws,
+                       cudaStream_t st);
+
+// DFMA throughput probe: returns total flops issued
+double launch_fp64_probe(double* sink, int iters, cudaStream_t st);
+
+}  // namespace rll

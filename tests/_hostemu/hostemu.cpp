@@ -1,0 +1,225 @@
+// hostemu.cpp -- TEST INFRASTRUCTURE: compiles the per-instance device arithmetic of
+// ratilqr.jl_b200/csrc/rl_core.cuh + rl_components.cuh with g++ and runs it on host memory, one
+// loop iteration per "thread".  It exists so that the kernel logic can be checked against the
+// oracle on a CPU-only box (`pytest -m "not gpu"`).  It is never linked into, loaded by, or
+// shipped with libratilqr_b200.so.
+#include <cstring>
+#include <vector>
+
+#include "../../ratilqr.jl_b200/csrc/rl_components.cuh"
+#include "../../ratilqr.jl_b200/csrc/rl_host.hpp"
+
+using namespace rl;
+
+template <class F> static int dispatch(int model_id, int cost_id, F&& fn) {
+#define X(MID, CID) if (model_id == MID && cost_id == CID) { fn(Dyn<MID>(), Cost<CID, Dyn<MID>::n, Dyn<MID>::m>()); return 0; }
+  RL_FOR_EACH_ILEQG_COMBO(X)
+  RL_FOR_EACH_ROLLOUT_ONLY_COMBO(X)
+#undef X
+  return -5;
+}
+
+template <int n, int m>
+static void ric(int N, int B, int optimise, const double* q, const double* qv, const double* Q, const double* r,
+                const double* R, const double* Pm, const double* A, const double* Bm, const rlh::WPrep& wp,
+                const double* theta, double mu_min, double delta_0, double* mu, double* delta, double* L, double* dl,
+                double* s, double* sv, double* S, int32_t* status, int32_t* restarts) {
+  for (int b = 0; b < B; ++b) {
+    int32_t nr = 0;
+    int st = comp_riccati<n, m>(N, optimise, q + (size_t)b * (N + 1), qv + (size_t)b * n * (N + 1), Q + (size_t)b * n * n * (N + 1),
+                                r + (size_t)b * m * N, R + (size_t)b * m * m * N, Pm + (size_t)b * m * n * N,
+                                A + (size_t)b * n * n * N, Bm + (size_t)b * n * m * N, wp.W.data(), wp.Winv.data(), wp.detW[0],
+                                theta[b], mu_min, delta_0, &mu[b], &delta[b], L + (size_t)b * m * n * N,
+                                dl ? dl + (size_t)b * m * N : nullptr, s + (size_t)b * (N + 1), sv + (size_t)b * n * (N + 1),
+                                S + (size_t)b * n * n * (N + 1), &nr);
+    if (status) status[b] = st;
+    if (restarts) restarts[b] = nr;
+  }
+}
+
+extern "C" {
+
+int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                                  const ratilqr_batch_in* in, ratilqr_ileqg_out* out) {
+  if (rlh::check_desc(desc, true)) return -1;
+  const int n = desc->n, m = desc->m, N = desc->N;
+  const size_t B = (size_t)in->P * in->K;
+  rlh::WPrep wp;
+  if (!rlh::prep_W(n, N, desc->W, desc->W_time_varying, wp)) return -2;
+  std::vector<double> X(2 * (size_t)(N + 1) * n * B), U(2 * (size_t)N * m * B), Lg((size_t)N * m * n * B, 0.0),
+      DL((size_t)N * m * B), value(B), mu(B), dcur(B), eps;
+  std::vector<int32_t> status(B), iters(B), trials(B), restarts(B), cur(B);
+  int cap = out->eps_hist ? out->eps_hist_cap : 0;
+  eps.assign(B * cap * 2 + 2, 0.0);
+  SolveParams P;
+  memset(&P, 0, sizeof(P));
+  P.N = N; P.B = (int)B; P.K = in->K;
+  for (int i = 0; i < 8; ++i) P.mp[i] = i < desc->n_model_params ? desc->model_params[i] : 0.0;
+  P.cost_params = desc->cost_params; P.ncp = desc->n_cost_params; P.cp_count = desc->cost_params_count;
+  P.W = wp.W.data(); P.Winv = wp.Winv.data(); P.detW = wp.detW.data(); P.W_tv = desc->W_time_varying;
+  P.x0 = in->x0; P.x0_count = in->x0_count; P.u_init = in->u_init; P.u_count = in->u_count; P.theta = in->theta;
+  P.mu_min = opts->mu_min; P.delta_0 = opts->delta_0; P.lambda = opts->lambda; P.d = opts->d;
+  P.iter_max = opts->iter_max; P.eps_auto = opts->adaptive_eps_init; P.eps_init = opts->eps_init; P.eps_min = opts->eps_min;
+  P.X = X.data(); P.U = U.data(); P.Lg = Lg.data(); P.DL = DL.data();
+  P.value = value.data(); P.status = status.data(); P.iters = iters.data(); P.trials = trials.data();
+  P.restarts = restarts.data(); P.mu_out = mu.data(); P.d_out = dcur.data(); P.cur = cur.data();
+  P.eps_hist = cap ? eps.data() : nullptr; P.eps_hist_cap = cap;
+  int rc = dispatch(desc->model_id, desc->cost_id, [&](auto D, auto CT) {
+    for (size_t b = 0; b < B; ++b) solve_instance<decltype(D), decltype(CT)>(P, b);
+  });
+  if (rc) return rc;
+  for (size_t b = 0; b < B; ++b) {
+    if (out->value) out->value[b] = value[b];
+    if (out->status) out->status[b] = status[b];
+    if (out->iters) out->iters[b] = iters[b];
+    if (out->trials) out->trials[b] = trials[b];
+    if (out->restarts) out->restarts[b] = restarts[b];
+    if (out->mu) out->mu[b] = mu[b];
+    if (out->d_current) out->d_current[b] = dcur[b];
+    size_t c = cur[b];
+    if (out->x) for (int e = 0; e < n * (N + 1); ++e) out->x[b * n * (N + 1) + e] = X[(c * (N + 1) * n + e) * B + b];
+    if (out->l) for (int e = 0; e < m * N; ++e) out->l[b * m * N + e] = U[(c * N * m + e) * B + b];
+    if (out->L) for (int e = 0; e < m * n * N; ++e) out->L[b * m * n * N + e] = Lg[(size_t)e * B + b];
+  }
+  if (cap) memcpy(out->eps_hist, eps.data(), B * cap * 16);
+  return 0;
+}
+
+int32_t hostemu_ce_costs(void*, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                         const ratilqr_batch_in* in, double kl, double* cost, int32_t* status) {
+  size_t B = (size_t)in->P * in->K;
+  std::vector<double> value(B);
+  std::vector<int32_t> st(B);
+  ratilqr_ileqg_out out;
+  memset(&out, 0, sizeof(out));
+  out.value = value.data(); out.status = st.data();
+  int rc = hostemu_ileqg_solve_batch(nullptr, desc, opts, in, &out);
+  if (rc) return rc;
+  for (size_t b = 0; b < B; ++b) { cost[b] = st[b] == 0 ? value[b] + kl / in->theta[b] : HUGE_VAL; if (status) status[b] = st[b]; }
+  return 0;
+}
+
+int32_t hostemu_rollout_open_batch(void*, const ratilqr_problem_desc* d, int32_t B, const double* x0, const double* u,
+                                   double* x, int32_t* status) {
+  return dispatch(d->model_id, d->cost_id, [&](auto D, auto) {
+    constexpr int n = decltype(D)::n, m = decltype(D)::m;
+    for (int b = 0; b < B; ++b) {
+      int st = comp_rollout_open<decltype(D)>(d->model_params, d->N, x0 + (size_t)b * n, u + (size_t)b * m * d->N, x + (size_t)b * n * (d->N + 1));
+      if (status) status[b] = st;
+    }
+  });
+}
+
+int32_t hostemu_rollout_closed_batch(void*, const ratilqr_problem_desc* d, int32_t B, const double* xbar, const double* l,
+                                     const double* L, double* xn, double* un, int32_t* status) {
+  return dispatch(d->model_id, d->cost_id, [&](auto D, auto CT) {
+    constexpr int n = decltype(D)::n, m = decltype(D)::m;
+    int N = d->N;
+    for (int b = 0; b < B; ++b) {
+      int st = comp_rollout_closed<decltype(D), decltype(CT)>(d->model_params, d->cost_params, N, xbar + (size_t)b * n * (N + 1),
+                                                             l + (size_t)b * m * N, L + (size_t)b * m * n * N, nullptr,
+                                                             xn + (size_t)b * n * (N + 1), un + (size_t)b * m * N, nullptr);
+      if (status) status[b] = st;
+    }
+  });
+}
+
+int32_t hostemu_integrate_cost_batch(void*, const ratilqr_problem_desc* d, int32_t B, const double* x, const double* u,
+                                     double* cost, int32_t* status) {
+  return dispatch(d->model_id, d->cost_id, [&](auto D, auto CT) {
+    constexpr int n = decltype(D)::n, m = decltype(D)::m;
+    int N = d->N;
+    for (int b = 0; b < B; ++b) {
+      double c = HUGE_VAL;
+      int st = comp_integrate_cost<decltype(D), decltype(CT)>(d->cost_params, N, x + (size_t)b * n * (N + 1), u + (size_t)b * m * N, &c);
+      cost[b] = st ? HUGE_VAL : c;
+      if (status) status[b] = st;
+    }
+  });
+}
+
+int32_t hostemu_linearize_batch(void*, const ratilqr_problem_desc* d, int32_t B, const double* x, const double* u,
+                                double* q, double* qv, double* Q, double* r, double* R, double* Pm, double* A, double* Bm,
+                                int32_t* status) {
+  if (rlh::check_desc(d, true)) return -1;
+  return dispatch(d->model_id, d->cost_id, [&](auto D, auto CT) {
+    constexpr int n = decltype(D)::n, m = decltype(D)::m;
+    int N = d->N;
+    for (int b = 0; b < B; ++b) {
+      int worst = 0;
+      for (int k = 0; k <= N; ++k) {
+        int st = comp_linearize_stage<decltype(D), decltype(CT)>(
+            d->model_params, d->cost_params, N, k, x + (size_t)b * n * (N + 1), u + (size_t)b * m * N, q + (size_t)b * (N + 1),
+            qv + (size_t)b * n * (N + 1), Q + (size_t)b * n * n * (N + 1), r + (size_t)b * m * N, R + (size_t)b * m * m * N,
+            Pm + (size_t)b * m * n * N, A + (size_t)b * n * n * N, Bm + (size_t)b * n * m * N);
+        if (st > worst) worst = st;
+      }
+      if (status) status[b] = worst;
+    }
+  });
+}
+
+int32_t hostemu_riccati_batch(void*, int32_t n, int32_t m, int32_t N, int32_t B, int32_t optimise, const double* q,
+                              const double* qv, const double* Q, const double* r, const double* R, const double* Pm,
+                              const double* A, const double* Bm, const double* W, const double* theta, double mu_min,
+                              double delta_0, double* mu, double* delta, double* L, double* dl, double* s, double* sv,
+                              double* S, int32_t* status, int32_t* restarts) {
+  rlh::WPrep wp;
+  if (!rlh::prep_W(n, N, W, 0, wp)) return -2;
+#define R_(NN, MM) if (n == NN && m == MM) { ric<NN, MM>(N, B, optimise, q, qv, Q, r, R, Pm, A, Bm, wp, theta, mu_min, delta_0, mu, delta, L, dl, s, sv, S, status, restarts); return 0; }
+  R_(2, 2) R_(2, 1) R_(4, 2) R_(4, 1) R_(12, 4)
+#undef R_
+  return -5;
+}
+
+int32_t hostemu_mc_rollout(void*, const ratilqr_problem_desc* d, int32_t P, const double* xbar, const double* l,
+                           const double* L, int32_t n_samples, const double* noise, uint64_t seed, double, double* J,
+                           double* stats, double* x_out) {
+  rlh::WPrep wp;
+  if (!rlh::prep_W(d->n, d->N, d->W, d->W_time_varying, wp)) return -2;
+  return dispatch(d->model_id, d->cost_id, [&](auto D, auto CT) {
+    constexpr int n = decltype(D)::n, m = decltype(D)::m;
+    int N = d->N;
+    for (int p = 0; p < P; ++p)
+      for (int s = 0; s < n_samples; ++s) {
+        size_t gi = (size_t)p * n_samples + s;
+        const double* cp = d->cost_params + (d->cost_params_count > 1 ? (size_t)p * d->n_cost_params : 0);
+        double c = HUGE_VAL;
+        std::vector<double> w((size_t)n * N);
+        if (noise) memcpy(w.data(), noise + gi * n * N, sizeof(double) * n * N);
+        else for (int k = 0; k < N; ++k) philox_noise<n>(seed, gi, (uint32_t)k, 0, 1.0, wp.cholW.data() + (d->W_time_varying ? (size_t)k * n * n : 0), &w[(size_t)k * n]);
+        int st = comp_rollout_closed<decltype(D), decltype(CT)>(d->model_params, cp, N, xbar + (size_t)p * n * (N + 1), l + (size_t)p * m * N,
+                                                               L + (size_t)p * m * n * N, w.data(),
+                                                               x_out ? x_out + gi * n * (N + 1) : nullptr, nullptr, &c);
+        J[gi] = st ? HUGE_VAL : c;
+      }
+    (void)stats;
+  });
+}
+
+int32_t hostemu_pets_costs(void*, const ratilqr_problem_desc* d, const ratilqr_generative_desc* gen, const double* x0,
+                           const double* controls, int32_t C, int32_t particles, const double* noise, uint64_t seed,
+                           double* cost) {
+  rlh::WPrep wp;
+  if (!rlh::prep_W(d->n, d->N, d->W, 0, wp)) return -2;
+  return dispatch(d->model_id, d->cost_id, [&](auto D, auto CT) {
+    constexpr int n = decltype(D)::n, m = decltype(D)::m;
+    int N = d->N;
+    int ne = gen && gen->n_ensemble > 1 ? gen->n_ensemble : 1;
+    int per = ne > 1 ? std::max(particles / ne, 1) : particles;
+    for (int ii = 0; ii < C; ++ii) {
+      double acc = 0.0;
+      for (int kk = 0; kk < particles; ++kk) {
+        const double* mp = d->model_params;
+        if (gen && gen->ensemble_params && ne > 1) mp = gen->ensemble_params + (size_t)std::min(kk / per, ne - 1) * d->n_model_params;
+        size_t gi = (size_t)ii * particles + kk;
+        acc += comp_pets_particle<decltype(D), decltype(CT)>(mp, d->cost_params, N, x0, controls + (size_t)ii * m * N,
+                                                            noise ? noise + gi * n * N : nullptr, seed, gi,
+                                                            gen ? gen->noise_kind : 0, gen ? gen->noise_scale : 1.0, wp.cholW.data());
+      }
+      cost[ii] = acc / particles;
+    }
+  });
+}
+
+}  // extern "C"

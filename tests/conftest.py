@@ -1,0 +1,44 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_be():
+    import oracle
+    return oracle.load()
+
+
+@pytest.fixture(scope="session")
+def hostemu_be():
+    from tests import _hostemu
+    return _hostemu.load()
+
+
+@pytest.fixture(scope="session")
+def gpu_be():
+    import ratilqr_b200 as R
+    be = R.new_backend(0)  # raises loudly if the .so is missing or no device can be opened
+    yield be
+    be.close()
+
+
+@pytest.fixture(params=["oracle", "hostemu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def backend(request):
+    """Every provider of the C ABI: the CPU oracle, the g++ build of the kernel arithmetic, the CUDA library."""
+    return request.getfixturevalue(request.param + "_be")
+
+
+@pytest.fixture(params=["oracle", pytest.param("gpu", marks=pytest.mark.gpu)])
+def full_backend(request):
+    """Providers that export the complete ABI (PETS refit / solve included)."""
+    return request.getfixturevalue(request.param + "_be")
