@@ -148,7 +148,9 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   P.trials = ctx->d_trials.as<int32_t>(); P.restarts = ctx->d_restarts.as<int32_t>();
   P.mu_out = ctx->d_mu.as<double>(); P.d_out = ctx->d_d.as<double>(); P.cur = ctx->d_cur.as<int32_t>();
   P.eps_hist = eps_cap > 0 ? ctx->d_eps.as<double>() : nullptr; P.eps_hist_cap = eps_cap;
-  ctx->model_id = desc->model_id; ctx->cost_id = desc->cost_id;
+  ctx->model_id = desc->model_id;
+  // structure-specialised kernel when the quadratic cost is diagonal (bit-identical results, fewer flops)
+  ctx->cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
   ctx->n = n; ctx->m = m; ctx->N = N; ctx->B = (int)B; ctx->eps_cap = eps_cap;
   ctx->staged = true;
   return 0;

@@ -88,6 +88,7 @@ RL_HD int comp_linearize_stage(const double* mp, const double* cp, int N, int k,
   for (int i = 0; i < n; ++i) xc[i] = x[(size_t)k * n + i];
   if (k == N) {
     double qq, qvl[n], Ql[n * n];
+    for (int i = 0; i < n * n; ++i) Ql[i] = 0.0;
     if (!CT::terminal(cp, xc, true, qq, qvl, Ql)) return RATILQR_ST_DOMAIN;
     q[N] = qq;
     for (int i = 0; i < n; ++i) qv[(size_t)N * n + i] = qvl[i];
@@ -99,6 +100,9 @@ RL_HD int comp_linearize_stage(const double* mp, const double* cp, int N, int k,
   }
   for (int j = 0; j < m; ++j) uc[j] = u[(size_t)k * m + j];
   double qq, qvl[n], Ql[n * n], rl_[m], Rl[m * m], Pl[m * n], Al[n * n], Bl[n * m];
+  for (int i = 0; i < n * n; ++i) Ql[i] = 0.0;  // structured costs only write their non-zero entries
+  for (int i = 0; i < m * m; ++i) Rl[i] = 0.0;
+  for (int i = 0; i < m * n; ++i) Pl[i] = 0.0;
   if (!CT::stage(cp, k, xc, uc, true, qq, qvl, Ql, rl_, Rl, Pl)) return RATILQR_ST_DOMAIN;
   D::jac(mp, xc, uc, Al, Bl);
   q[k] = qq;
@@ -146,14 +150,14 @@ RL_HD int comp_riccati(int N, int optimise, const double* q, const double* qv, c
       for (int i = 0; i < m * n; ++i) { Pl[i] = Pm[(size_t)k * m * n + i]; Bl[i] = Bm[(size_t)k * n * m + i]; }
       int rc;
       if (optimise) {
-        rc = riccati_stage<n, m, true, true>(theta, *mu, W, Winv, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
+        rc = riccati_stage<DenseTraits<n, m>, true, true>(theta, *mu, W, Winv, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
       } else {
         for (int i = 0; i < m * n; ++i) Ll[i] = L[(size_t)k * m * n + i];
         if (dl) {
           for (int i = 0; i < m; ++i) dll[i] = dl[(size_t)k * m + i];
-          rc = riccati_stage<n, m, false, true>(theta, *mu, W, Winv, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
+          rc = riccati_stage<DenseTraits<n, m>, false, true>(theta, *mu, W, Winv, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
         } else {
-          rc = riccati_stage<n, m, false, false>(theta, *mu, W, Winv, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
+          rc = riccati_stage<DenseTraits<n, m>, false, false>(theta, *mu, W, Winv, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
         }
       }
       if (rc == 1) { *restarts = nrestart; return optimise ? RATILQR_ST_M_NOT_PD_OPT : RATILQR_ST_M_NOT_PD_INIT; }

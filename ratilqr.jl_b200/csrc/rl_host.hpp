@@ -109,6 +109,27 @@ inline const char* check_desc(const ratilqr_problem_desc* d, bool differentiable
 
 }  // namespace rlh
 
+// internal cost id (see rl_core.cuh): QUADRATIC with diagonal Q, R, Qf and Pc == 0
+#ifndef RL_COST_QUAD_DIAG
+#define RL_COST_QUAD_DIAG 0x101
+#endif
+
+namespace rlh {
+// true when every parameter block of a QUADRATIC cost has diagonal Q, R, Qf and zero Pc
+inline bool quad_is_diag(const ratilqr_problem_desc* d) {
+  if (d->cost_id != RATILQR_COST_QUADRATIC) return false;
+  const int n = d->n, m = d->m;
+  for (int c = 0; c < d->cost_params_count; ++c) {
+    const double* p = d->cost_params + (size_t)c * d->n_cost_params;
+    const double *Q = p + 5 + n, *R = Q + n * n, *Pc = R + m * m, *Qf = Pc + n * m;
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) if (i != j && (Q[i + j * n] != 0.0 || Qf[i + j * n] != 0.0)) return false;
+    for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) if (i != j && R[i + j * m] != 0.0) return false;
+    for (int i = 0; i < n * m; ++i) if (Pc[i] != 0.0) return false;
+  }
+  return true;
+}
+}  // namespace rlh
+
 // (model, cost) pairs compiled into the library.  X(model_id, cost_id)
 #define RL_FOR_EACH_ILEQG_COMBO(X)                                   \
   X(RATILQR_MODEL_SINGLE_INTEGRATOR, RATILQR_COST_QUADRATIC)         \
@@ -119,6 +140,14 @@ inline const char* check_desc(const ratilqr_problem_desc* d, bool differentiable
   X(RATILQR_MODEL_CARTPOLE, RATILQR_COST_QUADRATIC)                  \
   X(RATILQR_MODEL_UNICYCLE, RATILQR_COST_QUADRATIC)                  \
   X(RATILQR_MODEL_QUADROTOR, RATILQR_COST_QUADRATIC)
+
+// structure-specialised solve kernels (host selects them when rlh::quad_is_diag)
+#define RL_FOR_EACH_DIAG_COMBO(X)                                    \
+  X(RATILQR_MODEL_SINGLE_INTEGRATOR, RL_COST_QUAD_DIAG)              \
+  X(RATILQR_MODEL_DOUBLE_INTEGRATOR, RL_COST_QUAD_DIAG)              \
+  X(RATILQR_MODEL_PENDULUM, RL_COST_QUAD_DIAG)                       \
+  X(RATILQR_MODEL_CARTPOLE, RL_COST_QUAD_DIAG)                       \
+  X(RATILQR_MODEL_UNICYCLE, RL_COST_QUAD_DIAG)
 
 // rollout-only pairs (PETS / MC) in addition to the ones above
 #define RL_FOR_EACH_ROLLOUT_ONLY_COMBO(X)                            \

@@ -6,6 +6,8 @@
 // rule fires.  No host round trips, no tensor cores (tiny FP64 matrices), per-stage matrices in
 // registers, trajectories in an SoA workspace (instance index fastest => every load/store of a
 // warp is one coalesced 256-byte transaction).
+#include <cstdlib>
+
 #include "rl_host.hpp"
 #include "rl_launch.hpp"
 
@@ -13,24 +15,50 @@ namespace rll {
 
 using namespace rl;
 
-template <class D, class CT>
-__global__ void __launch_bounds__(64) k_ileqg_solve(const __grid_constant__ SolveParams P) {
+template <class D, class CT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_ileqg_solve(const __grid_constant__ SolveParams P) {
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b < (size_t)P.B) solve_instance<D, CT>(P, b);
+}
+
+template <class D, class CT, int THREADS, int MINB>
+static void launch_shape(const SolveParams& P, cudaStream_t st) {
+  const int blocks = (P.B + THREADS - 1) / THREADS;
+  k_ileqg_solve<D, CT, THREADS, MINB><<<blocks, THREADS, 0, st>>>(P);
+}
+
+// launch shape = (threads per CTA, min resident CTAs per SM => register cap).  The default was chosen from
+// the sweep recorded in profiles/; RATILQR_SOLVE_SHAPE=<idx> overrides it for tuning runs.
+static int shape_override() {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("RATILQR_SOLVE_SHAPE"); v = e ? atoi(e) : -1; }
+  return v;
 }
 
 template <int MID, int CID>
 static void launch_one(const SolveParams& P, cudaStream_t st) {
   using D = Dyn<MID>;
   using CT = Cost<CID, D::n, D::m>;
-  const int threads = 64;
-  const int blocks = (P.B + threads - 1) / threads;
-  k_ileqg_solve<D, CT><<<blocks, threads, 0, st>>>(P);
+  if constexpr (MID == RATILQR_MODEL_UNICYCLE && CID == RL_COST_QUAD_DIAG) {
+    switch (shape_override()) {
+      case 0: launch_shape<D, CT, 64, 4>(P, st); return;    // 255 regs,  8 warps/SM
+      case 1: launch_shape<D, CT, 64, 6>(P, st); return;    // 168 regs, 12 warps/SM
+      case 2: launch_shape<D, CT, 64, 8>(P, st); return;    // 128 regs, 16 warps/SM
+      case 3: launch_shape<D, CT, 32, 8>(P, st); return;    // 255 regs, warp-sized CTAs
+      case 4: launch_shape<D, CT, 32, 12>(P, st); return;   // 168 regs
+      case 5: launch_shape<D, CT, 32, 16>(P, st); return;   // 128 regs
+      case 6: launch_shape<D, CT, 32, 20>(P, st); return;   // 96 regs, 20 warps/SM
+      default: launch_shape<D, CT, 32, 12>(P, st); return;
+    }
+  } else {
+    launch_shape<D, CT, 64, 4>(P, st);
+  }
 }
 
 int launch_solve(int model_id, int cost_id, const SolveParams& P, cudaStream_t st) {
 #define X(MID, CID) if (model_id == MID && cost_id == CID) { launch_one<MID, CID>(P, st); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)
+  RL_FOR_EACH_DIAG_COMBO(X)
 #undef X
   return -1;
 }

@@ -1,0 +1,24 @@
+"""Tuning sweep (GPU box): kernel-only time of the unicycle solve for each launch shape.
+usage: python scripts/tune_solve.py <shape> <problems> [reps]   -> one JSON line"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+shape, P = sys.argv[1], int(sys.argv[2])
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+os.environ["RATILQR_SOLVE_SHAPE"] = shape
+import numpy as np  # noqa: E402
+
+import bench  # noqa: E402
+import ratilqr_b200 as R  # noqa: E402
+
+be = R.new_backend(0)
+spec, x0, u, theta = bench.build_inputs(P, 0)
+be.stage(spec, x0, u, theta, P=P)
+be.run(2)
+ms = be.run(reps) / reps
+res = be.fetch()
+flops = float(np.sum(bench.algorithmic_flops(res["iters"], res["trials"])))
+print(json.dumps({"shape": shape, "problems": P, "ms": ms, "solves_per_s": theta.size / ms * 1e3,
+                  "tflops": flops / ms / 1e9, "ok": int((res["status"] == 0).sum()), "B": int(theta.size)}))

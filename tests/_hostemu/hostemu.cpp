@@ -15,6 +15,7 @@ template <class F> static int dispatch(int model_id, int cost_id, F&& fn) {
 #define X(MID, CID) if (model_id == MID && cost_id == CID) { fn(Dyn<MID>(), Cost<CID, Dyn<MID>::n, Dyn<MID>::m>()); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)
   RL_FOR_EACH_ROLLOUT_ONLY_COMBO(X)
+  RL_FOR_EACH_DIAG_COMBO(X)
 #undef X
   return -5;
 }
@@ -64,7 +65,8 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
   P.value = value.data(); P.status = status.data(); P.iters = iters.data(); P.trials = trials.data();
   P.restarts = restarts.data(); P.mu_out = mu.data(); P.d_out = dcur.data(); P.cur = cur.data();
   P.eps_hist = cap ? eps.data() : nullptr; P.eps_hist_cap = cap;
-  int rc = dispatch(desc->model_id, desc->cost_id, [&](auto D, auto CT) {
+  const int cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
+  int rc = dispatch(desc->model_id, cost_id, [&](auto D, auto CT) {
     for (size_t b = 0; b < B; ++b) solve_instance<decltype(D), decltype(CT)>(P, b);
   });
   if (rc) return rc;
