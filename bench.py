@@ -6,8 +6,9 @@
 
 Workload (config.workload = "c2_fleet"): BASELINE.json configs[1] -- 4-state unicycle, T=50, 1024 theta
 samples per problem -- replicated over P independent problems per GPU (x0 and goal drawn per problem, as
-in configs[4]) so that one step fills the device: 74 x 1024 = 75,776 iLEQG solves = two full waves of
-148 SMs x 256 resident instances.  A "step" = one batched solve of all instances (one kernel launch).
+in configs[4]) so that one step fills the device: 444 x 1024 = 454,656 iLEQG solves = eight full waves of
+148 SMs x 384 resident instances (12 warps/SM at 168 registers).  A "step" = one batched solve of all
+instances (one launch of the persistent solve kernel).
 Weak scaling: every rank owns P problems; there is no data-path collective (instances are independent).
 
 value  : solves/s, kernel only, inputs resident in HBM, CUDA events on the library's stream.
@@ -129,7 +130,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--problems", type=int, default=74, help="independent unicycle problems per GPU (x 1024 theta each)")
+    ap.add_argument("--problems", type=int, default=444, help="independent unicycle problems per GPU (x 1024 theta each)")
     ap.add_argument("--cpu-sample-problems", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -140,7 +141,8 @@ def main():
     config = {"workload": "c2_fleet", "model": None, "dynamics": "unicycle n=4 m=2", "horizon": HORIZON,
               "thetas_per_problem": THETAS, "problems_per_gpu": args.problems,
               "solves_per_step_per_gpu": args.problems * THETAS, "kl_bound": 0.1,
-              "l2_policy": "inputs_larger_than_l2 (672 MB SoA workspace per step vs 126 MB L2)", "parallelism": f"dp{world}"}
+              "l2_policy": f"inputs_larger_than_l2 ({args.problems * THETAS * 8864 / 1e6:.0f} MB SoA workspace per step vs 126 MB L2)",
+              "parallelism": f"dp{world}"}
     config.pop("model")
 
     if args.impl == "reference":

@@ -41,7 +41,7 @@ struct ratilqr_ctx {
   int model_id = 0, cost_id = 0, n = 0, m = 0, N = 0, B = 0, eps_cap = 0;
   rl::SolveParams sp;
   DBuf d_cp, d_W, d_Winv, d_detW, d_x0, d_u, d_theta, d_X, d_U, d_Lg, d_DL;
-  DBuf d_value, d_status, d_iters, d_trials, d_restarts, d_mu, d_d, d_cur, d_eps;
+  DBuf d_value, d_status, d_iters, d_trials, d_restarts, d_mu, d_d, d_cur, d_eps, d_perm;
   DBuf d_out1, d_out2, d_out3;  // host-layout staging for x, l, L
   // scratch for component calls
   DBuf s[16];
@@ -148,6 +148,14 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   P.trials = ctx->d_trials.as<int32_t>(); P.restarts = ctx->d_restarts.as<int32_t>();
   P.mu_out = ctx->d_mu.as<double>(); P.d_out = ctx->d_d.as<double>(); P.cur = ctx->d_cur.as<int32_t>();
   P.eps_hist = eps_cap > 0 ? ctx->d_eps.as<double>() : nullptr; P.eps_hist_cap = eps_cap;
+  // warp-homogeneous scheduling: lanes of a warp get neighbouring theta of one problem
+  CU(ctx->d_perm.reserve(B * 4));
+  if (rll::launch_sort_theta(P.theta, in->P, in->K, ctx->d_perm.as<int32_t>(), ctx->stream) == 0) {
+    if (int rc = check_launch(ctx, "k_sort_theta")) return rc;
+    P.perm = ctx->d_perm.as<int32_t>();
+  } else {
+    P.perm = nullptr;
+  }
   ctx->model_id = desc->model_id;
   // structure-specialised kernel when the quadratic cost is diagonal (bit-identical results, fewer flops)
   ctx->cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
@@ -185,7 +193,7 @@ static int fetch_internal(ratilqr_ctx* ctx, ratilqr_ileqg_out* out) {
   if (out->l) { CU(ctx->d_out2.reserve((size_t)m * N * B * 8)); dl = ctx->d_out2.as<double>(); }
   if (out->L) { CU(ctx->d_out3.reserve((size_t)m * n * N * B * 8)); dL = ctx->d_out3.as<double>(); }
   if (dx || dl || dL) {
-    rll::launch_gather(n, m, N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.cur, dx, dl, dL, st);
+    rll::launch_gather(n, m, N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.cur, ctx->sp.perm, dx, dl, dL, st);
     if (int rc = check_launch(ctx, "k_gather", (dx ? 1 : 0) + (dl ? 1 : 0) + (dL ? 1 : 0))) return rc;
   }
 #define DOWN(dst, src, bytes) if (dst) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))
@@ -247,7 +255,7 @@ int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DBuf* all[] = {&ctx->d_cp, &ctx->d_W, &ctx->d_Winv, &ctx->d_detW, &ctx->d_x0, &ctx->d_u, &ctx->d_theta, &ctx->d_X,
                  &ctx->d_U, &ctx->d_Lg, &ctx->d_DL, &ctx->d_value, &ctx->d_status, &ctx->d_iters, &ctx->d_trials,
-                 &ctx->d_restarts, &ctx->d_mu, &ctx->d_d, &ctx->d_cur, &ctx->d_eps, &ctx->d_out1, &ctx->d_out2,
+                 &ctx->d_restarts, &ctx->d_mu, &ctx->d_d, &ctx->d_cur, &ctx->d_eps, &ctx->d_perm, &ctx->d_out1, &ctx->d_out2,
                  &ctx->d_out3, &ctx->d_cost};
   for (DBuf* b : all) b->release();
   for (DBuf& b : ctx->s) b.release();

@@ -48,6 +48,9 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
       case 4: launch_shape<D, CT, 32, 12>(P, st); return;   // 168 regs
       case 5: launch_shape<D, CT, 32, 16>(P, st); return;   // 128 regs
       case 6: launch_shape<D, CT, 32, 20>(P, st); return;   // 96 regs, 20 warps/SM
+      case 7: launch_shape<D, CT, 32, 14>(P, st); return;   // 144 regs
+      case 8: launch_shape<D, CT, 32, 13>(P, st); return;   // 152 regs
+      case 9: launch_shape<D, CT, 32, 10>(P, st); return;   // 200 regs
       default: launch_shape<D, CT, 32, 12>(P, st); return;
     }
   } else {
@@ -66,8 +69,8 @@ int launch_solve(int model_id, int cost_id, const SolveParams& P, cudaStream_t s
 // ---- outputs: SoA workspace -> host layout -----------------------------------------------
 // src element e of instance b: src[(buf_b * E + e) * B + b]  (buf_b = cur[b] when double-buffered)
 // dst: dst[b * E + e].  32x32 tiles through shared memory: coalesced on both sides.
-__global__ void k_gather(const double* __restrict__ src, const int32_t* __restrict__ cur, int E, int B, int skipE,
-                         double* __restrict__ dst) {
+__global__ void k_gather(const double* __restrict__ src, const int32_t* __restrict__ cur,
+                         const int32_t* __restrict__ perm, int E, int B, int skipE, double* __restrict__ dst) {
   __shared__ double tile[32][33];
   int b0 = blockIdx.x * 32, e0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -80,16 +83,55 @@ __global__ void k_gather(const double* __restrict__ src, const int32_t* __restri
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     int b = b0 + r, e = e0 + threadIdx.x;
-    if (e < E && b < B) dst[(size_t)b * E + e] = tile[threadIdx.x][r];
+    if (e < E && b < B) dst[(size_t)(perm ? perm[b] : b) * E + e] = tile[threadIdx.x][r];
   }
 }
 
 void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg,
-                   const int32_t* cur, double* x_out, double* l_out, double* L_out, cudaStream_t st) {
+                   const int32_t* cur, const int32_t* perm, double* x_out, double* l_out, double* L_out, cudaStream_t st) {
   dim3 th(32, 8);
-  if (x_out) { int E = n * (N + 1); k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(X, cur, E, B, 0, x_out); }
-  if (l_out) { int E = m * N; k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(U, cur, E, B, 0, l_out); }
-  if (L_out) { int E = m * n * N; k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(Lg, nullptr, E, B, 0, L_out); }
+  if (x_out) { int E = n * (N + 1); k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(X, cur, perm, E, B, 0, x_out); }
+  if (l_out) { int E = m * N; k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(U, cur, perm, E, B, 0, l_out); }
+  if (L_out) { int E = m * n * N; k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(Lg, nullptr, perm, E, B, 0, L_out); }
+}
+
+// ---- theta sort: one CTA per problem, bitonic sort of (theta, index) in shared memory ---------------
+// perm[p*K + r] = p*K + (index of the r-th smallest theta of problem p); ties broken by index (total order).
+__global__ void __launch_bounds__(1024) k_sort_theta(const double* __restrict__ theta, int K, int Kpad, int32_t* __restrict__ perm) {
+  extern __shared__ unsigned char smem_raw[];
+  double* key = reinterpret_cast<double*>(smem_raw);
+  int32_t* idx = reinterpret_cast<int32_t*>(key + Kpad);
+  const size_t base = (size_t)blockIdx.x * K;
+  for (int i = threadIdx.x; i < Kpad; i += blockDim.x) {
+    double t = i < K ? theta[base + i] : HUGE_VAL;
+    key[i] = (t != t) ? HUGE_VAL : t;  // NaN sorts last
+    idx[i] = i;
+  }
+  __syncthreads();
+  for (int k = 2; k <= Kpad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < Kpad; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          bool up = (i & k) == 0;
+          double a = key[i], b = key[ixj];
+          int ia = idx[i], ib = idx[ixj];
+          bool a_gt_b = (a > b) || (a == b && ia > ib);
+          if (a_gt_b == up) { key[i] = b; key[ixj] = a; idx[i] = ib; idx[ixj] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) perm[base + i] = (int32_t)(base + idx[i]);
+}
+
+int launch_sort_theta(const double* theta, int P, int K, int32_t* perm, cudaStream_t st) {
+  if (K < 2 || K > 4096) return -1;  // nothing to gain / does not fit one CTA: caller keeps the identity
+  int Kpad = 2;
+  while (Kpad < K) Kpad <<= 1;
+  int threads = Kpad / 2 < 1024 ? (Kpad / 2 < 32 ? 32 : Kpad / 2) : 1024;
+  k_sort_theta<<<P, threads, (size_t)Kpad * 12, st>>>(theta, K, Kpad, perm);
+  return 0;
 }
 
 // ---- FP64 FMA throughput probe ----------------------------------------------------------------

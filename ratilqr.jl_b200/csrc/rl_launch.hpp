@@ -13,7 +13,10 @@ int launch_solve(int model_id, int cost_id, const rl::SolveParams& P, cudaStream
 
 // SoA workspace -> host-layout outputs (x, l, L), tile transpose through shared memory
 void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg, const int32_t* cur,
-                   double* x_out, double* l_out, double* L_out, cudaStream_t st);
+                   const int32_t* perm, double* x_out, double* l_out, double* L_out, cudaStream_t st);
+
+// per-problem ascending sort of theta -> slot-to-instance permutation; returns -1 when not applicable
+int launch_sort_theta(const double* theta, int P, int K, int32_t* perm, cudaStream_t st);
 
 struct CompArgs {
   int model_id, cost_id, n, m, N, B;

@@ -15,10 +15,14 @@ import ratilqr_b200 as R  # noqa: E402
 
 be = R.new_backend(0)
 spec, x0, u, theta = bench.build_inputs(P, 0)
+if os.environ.get("TUNE_SORT_THETA"):
+    theta = np.sort(theta.reshape(P, -1), axis=1).reshape(-1)
 be.stage(spec, x0, u, theta, P=P)
 be.run(2)
 ms = be.run(reps) / reps
 res = be.fetch()
 flops = float(np.sum(bench.algorithmic_flops(res["iters"], res["trials"])))
 print(json.dumps({"shape": shape, "problems": P, "ms": ms, "solves_per_s": theta.size / ms * 1e3,
-                  "tflops": flops / ms / 1e9, "ok": int((res["status"] == 0).sum()), "B": int(theta.size)}))
+                  "tflops": flops / ms / 1e9, "ok": int((res["status"] == 0).sum()), "B": int(theta.size),
+                  "sorted": bool(os.environ.get("TUNE_SORT_THETA")), "iters_minmax": [int(res["iters"].min()), int(res["iters"].max())],
+                  "trials_minmax": [int(res["trials"].min()), int(res["trials"].max())]}))

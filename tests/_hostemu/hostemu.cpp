@@ -3,6 +3,7 @@
 // loop iteration per "thread".  It exists so that the kernel logic can be checked against the
 // oracle on a CPU-only box (`pytest -m "not gpu"`).  It is never linked into, loaded by, or
 // shipped with libratilqr_b200.so.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -65,6 +66,14 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
   P.value = value.data(); P.status = status.data(); P.iters = iters.data(); P.trials = trials.data();
   P.restarts = restarts.data(); P.mu_out = mu.data(); P.d_out = dcur.data(); P.cur = cur.data();
   P.eps_hist = cap ? eps.data() : nullptr; P.eps_hist_cap = cap;
+  // same slot->instance permutation as the device library (theta ascending within each problem)
+  std::vector<int32_t> perm(B);
+  for (int p = 0; p < in->P; ++p) {
+    int32_t* pp = perm.data() + (size_t)p * in->K;
+    for (int i = 0; i < in->K; ++i) pp[i] = (int32_t)((size_t)p * in->K + i);
+    std::stable_sort(pp, pp + in->K, [&](int32_t a, int32_t b2) { return in->theta[a] < in->theta[b2]; });
+  }
+  P.perm = in->K >= 2 ? perm.data() : nullptr;
   const int cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
   int rc = dispatch(desc->model_id, cost_id, [&](auto D, auto CT) {
     for (size_t b = 0; b < B; ++b) solve_instance<decltype(D), decltype(CT)>(P, b);
@@ -78,10 +87,10 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
     if (out->restarts) out->restarts[b] = restarts[b];
     if (out->mu) out->mu[b] = mu[b];
     if (out->d_current) out->d_current[b] = dcur[b];
-    size_t c = cur[b];
-    if (out->x) for (int e = 0; e < n * (N + 1); ++e) out->x[b * n * (N + 1) + e] = X[(c * (N + 1) * n + e) * B + b];
-    if (out->l) for (int e = 0; e < m * N; ++e) out->l[b * m * N + e] = U[(c * N * m + e) * B + b];
-    if (out->L) for (int e = 0; e < m * n * N; ++e) out->L[b * m * n * N + e] = Lg[(size_t)e * B + b];
+    size_t c = cur[b], inst = P.perm ? (size_t)P.perm[b] : b;  // b is the slot here
+    if (out->x) for (int e = 0; e < n * (N + 1); ++e) out->x[inst * n * (N + 1) + e] = X[(c * (N + 1) * n + e) * B + b];
+    if (out->l) for (int e = 0; e < m * N; ++e) out->l[inst * m * N + e] = U[(c * N * m + e) * B + b];
+    if (out->L) for (int e = 0; e < m * n * N; ++e) out->L[inst * m * n * N + e] = Lg[(size_t)e * B + b];
   }
   if (cap) memcpy(out->eps_hist, eps.data(), B * cap * 16);
   return 0;
