@@ -11,7 +11,8 @@ import math
 import numpy as np
 
 from . import _lib
-from .ileqg import ILEQGSolver, _ascii_kw, _stack, solve_
+from .ileqg import ILEQGSolver, _stack
+from .ileqg import solve_ as ileqg_solve_
 
 
 class InjectedNormals:
@@ -148,7 +149,7 @@ def solve_(ce, problem, x_0, u_array, rng, verbose=False, serial=False, **kw):
     while True:
         try:
             ileqg = ILEQGSolver(problem, backend=ce._be(), **ce.ileqg_kwargs())
-            x_array, l_array, L_array, value, _ = solve_(ileqg, problem, x_0, u_array, theta=theta_opt, verbose=False)
+            x_array, l_array, L_array, value, _ = ileqg_solve_(ileqg, problem, x_0, u_array, theta=theta_opt, verbose=False)
             if kl_bound > 0:
                 return theta_opt, x_array, l_array, L_array, value + kl_bound / theta_opt, theta_min, theta_max
             return theta_opt, x_array, l_array, L_array, value, 0.0, 0.0

@@ -109,10 +109,24 @@ def step_(s, problem, x, rng, use_true_model=False, verbose=False, serial=False,
 
 
 def solve_(s, problem, x_0, rng, use_true_model=False, verbose=False, serial=True, z_inject=None, noise=None):
-    """solve! (pets.jl:270-281) -> (μ_array, Σ_array); the whole loop runs on the device.
-    rng: int seed -> on-device Philox;  z_inject (m,N,C,iter_max) + noise (n,N,particles,C,iter_max) -> exact."""
+    """solve! (pets.jl:270-281) -> (μ_array, Σ_array); the whole CEM loop runs on the device.
+    rng: int seed -> on-device Philox;  numpy Generator -> z and noise are drawn on the host in the reference's
+    consumption order (pets.jl:208-216 then :137-152, per iteration) and injected;
+    z_inject (m,N,C,iter_max) + noise (n,N,particles,C,iter_max) -> exact replay."""
     initialize_(s)
-    seed = int(rng) if isinstance(rng, (int, np.integer)) else int(rng.integers(0, 2 ** 62)) if rng is not None else 0
+    seed = 0
+    if isinstance(rng, (int, np.integer)):
+        seed = int(rng)
+    elif rng is not None and z_inject is None:
+        m, N, C, Kp = s.mu_array[0].size, s.N, s.num_control_samples, s.num_trajectory_samples
+        n = problem.f_stochastic.dynamics.n
+        z_inject = np.zeros((m, N, C, s.iter_max))
+        noise = np.zeros((n, N, Kp, C, s.iter_max))
+        for it in range(s.iter_max):
+            for ii in range(C):
+                for tt in range(N):
+                    z_inject[:, tt, ii, it] = rng.standard_normal(m)
+            noise[..., it] = _noise_for(problem, s, rng, C)
     mu, Sg = s._be().pets_solve(problem.spec(), np.asarray(x_0, float), _stack(s.mu_array), _stack(s.Sigma_array),
                                 s.num_control_samples, s.num_trajectory_samples, s.num_elite, s.iter_max,
                                 s.smoothing_factor, z_inject=z_inject, noise=noise, seed=seed,

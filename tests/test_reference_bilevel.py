@@ -1,0 +1,151 @@
+"""test/cross_entropy_bilevel_optimization_test.jl and test/nelder_mead_bilevel_optimization_test.jl of the
+reference re-expressed against the host mirror; plus whole-solve parity of the host loops (Python + batched
+device fan-out) against the oracle's independent C++ restatement of the same Julia files."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import ratilqr_b200 as R
+from ratilqr_b200 import cross_entropy as CE
+from ratilqr_b200 import nelder_mead as NM
+from ratilqr_b200 import workloads as wl
+from ratilqr_b200._capi import IleqgOpts, ProblemDesc, make_opts
+
+dp = C.POINTER(C.c_double)
+
+
+class OracleCEOpts(C.Structure):
+    _fields_ = [("mu_init", C.c_double), ("sigma_init", C.c_double), ("num_samples", C.c_int32), ("num_elite", C.c_int32),
+                ("iter_max", C.c_int32), ("lam", C.c_double), ("use_theta_max", C.c_int32)]
+
+
+class OracleNMOpts(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double), ("eps", C.c_double), ("lam", C.c_double),
+                ("iter_max", C.c_int32), ("theta_high_init", C.c_double), ("theta_low_init", C.c_double),
+                ("c_high", C.c_double), ("c_low", C.c_double), ("has_c_high", C.c_int32), ("has_c_low", C.c_int32)]
+
+
+def _problem():
+    prob, x0, u = wl.c1_problem()
+    return prob, x0, [u[:, k].copy() for k in range(u.shape[1])]
+
+
+def test_ce_reference_suite(backend):
+    """cross_entropy_bilevel_optimization_test.jl:10-41"""
+    prob, x0, u_array = _problem()
+    solver = R.CrossEntropyBilevelOptimizationSolver(num_samples=3, backend=backend)
+    CE.initialize_(solver)
+    theta_array = [0.1, 0.3, 0.43]
+    costs = CE.compute_cost(solver, prob, x0, u_array, theta_array, 1.0)          # :27
+    costs_test = CE.compute_cost_serial(solver, prob, x0, u_array, theta_array, 1.0)
+    assert np.allclose(costs, costs_test)                                         # :30
+    # BASELINE.md section 4 anchors (survey-time numpy restatement, not Julia)
+    assert np.allclose(costs, [11.002908466254208, 4.33624364124029, 3.3284929065983375], rtol=1e-12)
+    th = CE.get_positive_samples(0.0, 1.0, 10, np.random.default_rng(123))        # :32-33
+    assert np.all(th > 0.0) and len(th) == 10
+    rng = np.random.default_rng(12344)
+    theta_opt, x_array, l_array, L_array, c_opt, th_min, th_max = CE.solve_(solver, prob, x0, u_array, rng, kl_bound=1.0)
+    assert not math.isinf(c_opt) and not math.isnan(theta_opt)                    # :38-39
+    assert 0 < th_min <= th_max
+    # kl_bound == 0 reduces to iLQG (:386-389,408)
+    t0, _, _, _, v0, a, b = CE.solve_(solver, prob, x0, u_array, rng, kl_bound=0.0)
+    assert t0 == 0.0 and a == 0.0 and b == 0.0 and np.isclose(v0, 1.0029075497782471, rtol=1e-12)
+
+
+def test_nm_reference_suite(backend):
+    """nelder_mead_bilevel_optimization_test.jl:11-32"""
+    prob, x0, u_array = _problem()
+    nm = R.NelderMeadBilevelOptimizationSolver(iter_max=20, eps=1e-3, theta_high_init=10.0, theta_low_init=1e-8, backend=backend)
+    theta_opt, x_array, l_array, L_array, c_opt = NM.solve_(nm, prob, x0, u_array, kl_bound=1.0)
+    assert not math.isinf(c_opt) and not math.isnan(theta_opt)                    # :25-26
+    c_low_init = NM.compute_cost_worker(nm, prob, x0, u_array, nm.theta_low_init, 1.0)
+    c_high_init = NM.compute_cost_worker(nm, prob, x0, u_array, nm.theta_high_init, 1.0)
+    assert not math.isinf(c_low_init) and not math.isinf(c_high_init)              # :29
+    assert c_opt <= c_low_init and c_opt <= c_high_init                            # :30-31
+    # SURVEY Appendix B anchor: 5 NM iterations, theta_opt = 29.99999998, c_opt = 1.0367995862438515
+    assert nm.iter_current == 5 and np.isclose(theta_opt, 29.99999998, rtol=1e-9) and np.isclose(c_opt, 1.0367995862438515, rtol=1e-9)
+
+
+def test_nm_speculative_equals_serial(backend):
+    prob, x0, u_array = _problem()
+    res = []
+    for spec in (True, False):
+        nm = R.NelderMeadBilevelOptimizationSolver(iter_max=20, eps=1e-3, theta_high_init=10.0, theta_low_init=1e-8,
+                                                   backend=backend, speculative=spec)
+        out = NM.solve_(nm, prob, x0, u_array, kl_bound=1.0)
+        res.append((out[0], out[4], nm.iter_current, nm.n_evals, nm.theta_high, nm.c_high, nm.c_low))
+    assert res[0] == res[1]  # identical simplex history, vertices and evaluation count
+
+
+def _desc(spec):
+    return spec.desc()
+
+
+@pytest.mark.parametrize("kl", [1.0, 0.05])
+def test_ce_whole_solve_matches_oracle_restatement(backend, oracle_be, kl):
+    """Host CE loop (Python) + batched fan-out vs the oracle's C++ restatement of solve! with the same
+    injected standard-normal stream (Julia's rng cannot be reproduced)."""
+    prob, x0, u_array = _problem()
+    spec = prob.spec()
+    z = np.random.Generator(np.random.Philox(key=99)).standard_normal(4000)
+    solver = R.CrossEntropyBilevelOptimizationSolver(num_samples=8, num_elite=3, iter_max=4, mu_init=20.0, sigma_init=15.0,
+                                                     backend=backend)
+    stream = CE.InjectedNormals(z)
+    got = CE.solve_(solver, prob, x0, u_array, stream, kl_bound=kl)
+    # oracle side
+    d = _desc(spec)
+    opts = make_opts()
+    ce = OracleCEOpts(20.0, 15.0, 8, 3, 4, 0.5, 0)
+    n, m, N = spec.n, spec.m, spec.N
+    outs = [C.c_double() for _ in range(6)]
+    nz = C.c_int64()
+    st = C.c_int32()
+    x = np.zeros((n, N + 1), order="F"); l = np.zeros((m, N), order="F"); L = np.zeros((m, n, N), order="F")
+    u = np.ascontiguousarray(np.stack(u_array, axis=-1).ravel(order="F"))
+    f = oracle_be.raw.oracle_ce_solve
+    f.restype = C.c_int32
+    rc = f(C.byref(d), C.byref(opts), C.byref(ce), x0.ctypes.data_as(dp), u.ctypes.data_as(dp), C.c_double(kl),
+           z.ctypes.data_as(dp), C.c_int64(z.size), *[C.byref(o) for o in outs[:6]], C.byref(nz),
+           x.ctypes.data_as(dp), l.ctypes.data_as(dp), L.ctypes.data_as(dp), C.byref(st))
+    assert rc == 0 and st.value == 0
+    theta_opt, value, th_min, th_max, mu, sigma = [o.value for o in outs]
+    assert stream.i == nz.value                         # same number of draws consumed => same redraw history
+    assert np.isclose(got[0], theta_opt, rtol=1e-9) and np.isclose(got[4], value, rtol=1e-9)
+    assert np.isclose(got[5], th_min, rtol=1e-12) and np.isclose(got[6], th_max, rtol=1e-12)
+    assert np.isclose(solver.mu, mu, rtol=1e-9) and np.isclose(solver.sigma, sigma, rtol=1e-9)
+    assert np.isclose(solver.mu_init, ce.mu_init) and np.isclose(solver.sigma_init, ce.sigma_init)
+    assert np.allclose(np.stack(got[1], -1), x, rtol=1e-9, atol=1e-12)
+    assert np.allclose(np.stack(got[3], -1), L, rtol=1e-9, atol=1e-12)
+
+
+def test_nm_whole_solve_matches_oracle_restatement(backend, oracle_be):
+    prob, x0, u_array = _problem()
+    spec = prob.spec()
+    nm = R.NelderMeadBilevelOptimizationSolver(iter_max=20, eps=1e-3, theta_high_init=10.0, theta_low_init=1e-8, backend=backend)
+    got = NM.solve_(nm, prob, x0, u_array, kl_bound=1.0)
+    d = _desc(spec)
+    opts = make_opts()
+    o = OracleNMOpts(1.0, 2.0, 0.5, 1e-3, 0.5, 20, 10.0, 1e-8, 0.0, 0.0, 0, 0)
+    n, m, N = spec.n, spec.m, spec.N
+    th, val = C.c_double(), C.c_double()
+    it, ev, st = C.c_int32(), C.c_int32(), C.c_int32()
+    x = np.zeros((n, N + 1), order="F"); l = np.zeros((m, N), order="F"); L = np.zeros((m, n, N), order="F")
+    u = np.ascontiguousarray(np.stack(u_array, axis=-1).ravel(order="F"))
+    f = oracle_be.raw.oracle_nm_solve
+    f.restype = C.c_int32
+    rc = f(C.byref(d), C.byref(opts), C.byref(o), x0.ctypes.data_as(dp), u.ctypes.data_as(dp), C.c_double(1.0),
+           C.byref(th), C.byref(val), C.byref(it), C.byref(ev), x.ctypes.data_as(dp), l.ctypes.data_as(dp),
+           L.ctypes.data_as(dp), C.byref(st))
+    assert rc == 0 and st.value == 0
+    assert nm.iter_current == it.value and nm.n_evals == ev.value == 12  # 12 cost evaluations
+    assert np.isclose(got[0], th.value, rtol=1e-12) and np.isclose(got[4], val.value, rtol=1e-9)
+    assert np.isclose(nm.theta_high_init, o.theta_high_init) and np.isclose(nm.c_low, o.c_low, rtol=1e-9)
+    assert np.allclose(np.stack(got[1], -1), x, rtol=1e-9, atol=1e-12)
+    # second solve! on the same solver reuses the stale vertex costs (reference quirk)
+    got2 = NM.solve_(nm, prob, x0, u_array, kl_bound=1.0)
+    rc = f(C.byref(d), C.byref(opts), C.byref(o), x0.ctypes.data_as(dp), u.ctypes.data_as(dp), C.c_double(1.0),
+           C.byref(th), C.byref(val), C.byref(it), C.byref(ev), x.ctypes.data_as(dp), l.ctypes.data_as(dp),
+           L.ctypes.data_as(dp), C.byref(st))
+    assert np.isclose(got2[0], th.value, rtol=1e-12) and np.isclose(got2[4], val.value, rtol=1e-9)
