@@ -236,6 +236,13 @@ def main():
         except OSError:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None  # dram__bytes_read+write of the solve kernel from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "solve_traffic.json")))
+            if tj.get("problems_per_gpu") == P:
+                traffic = tj["dram_bytes_per_launch"]
+        except OSError:
+            pass
         ach_gbs = byts / (ms_per_step * 1e-3) / 1e9
         # the exact configs[1] shape: ONE problem x 1024 theta (latency-bound: 32 warps on a 148-SM device)
         s1, x01, u1, th1 = build_inputs(1, 0)
@@ -251,7 +258,7 @@ def main():
                "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "api": "ratilqr_ce_costs (compute_cost), host buffers in, cost+status vectors out"},
                "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                            "traffic": None, "kernel": "k_ileqg_solve<unicycle, quadratic>",
+                            "traffic": traffic, "algorithmic_bytes_per_launch": byts, "kernel": "k_ileqg_solve<unicycle, quadratic>",
                             "peak_source": "DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 figure)",
                             "flops_per_launch": flops},
                "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
