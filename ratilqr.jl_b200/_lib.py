@@ -6,7 +6,7 @@ import os
 from ._capi import CApi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libratilqr_b200.so")
+LIB_PATH = os.environ.get("RATILQR_B200_LIB") or os.path.join(_HERE, "csrc", "libratilqr_b200.so")  # env override: tuning A/B runs
 
 _dll = None
 _default = None

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -148,6 +149,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   P.trials = ctx->d_trials.as<int32_t>(); P.restarts = ctx->d_restarts.as<int32_t>();
   P.mu_out = ctx->d_mu.as<double>(); P.d_out = ctx->d_d.as<double>(); P.cur = ctx->d_cur.as<int32_t>();
   P.eps_hist = eps_cap > 0 ? ctx->d_eps.as<double>() : nullptr; P.eps_hist_cap = eps_cap;
+  { const char* e = getenv("RATILQR_NO_STAGE"); P.use_stage = (e && e[0] == '1') ? 0 : 1; }
   // warp-homogeneous scheduling: lanes of a warp get neighbouring theta of one problem
   CU(ctx->d_perm.reserve(B * 4));
   if (rll::launch_sort_theta(P.theta, in->P, in->K, ctx->d_perm.as<int32_t>(), ctx->stream) == 0) {

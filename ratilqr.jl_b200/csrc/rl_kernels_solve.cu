@@ -6,6 +6,7 @@
 // rule fires.  No host round trips, no tensor cores (tiny FP64 matrices), per-stage matrices in
 // registers, trajectories in an SoA workspace (instance index fastest => every load/store of a
 // warp is one coalesced 256-byte transaction).
+#include <cstdio>
 #include <cstdlib>
 
 #include "rl_host.hpp"
@@ -17,14 +18,35 @@ using namespace rl;
 
 template <class D, class CT, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_ileqg_solve(const __grid_constant__ SolveParams P) {
+  extern __shared__ double stage_area[];  // [2][RL_STAGE_NV][THREADS] doubles when staging is enabled, else empty
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < (size_t)P.B) solve_instance<D, CT>(P, b);
+  Stage sg;
+  sg.base = (UseStage<D>::value && P.use_stage) ? stage_area + threadIdx.x : nullptr;
+  sg.stride = THREADS;
+  if (b < (size_t)P.B) solve_instance<D, CT>(P, b, sg);
 }
 
 template <class D, class CT, int THREADS, int MINB>
 static void launch_shape(const SolveParams& P, cudaStream_t st) {
   const int blocks = (P.B + THREADS - 1) / THREADS;
-  k_ileqg_solve<D, CT, THREADS, MINB><<<blocks, THREADS, 0, st>>>(P);
+  const size_t smem = UseStage<D>::value ? (size_t)2 * RL_STAGE_NV * THREADS * sizeof(double) : 0;
+  static bool configured = false;
+  if (!configured) {
+    configured = true;
+    auto kfn = k_ileqg_solve<D, CT, THREADS, MINB>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 0) {
+      // the default L1/shared split admits only a few staging CTAs per SM: ask for what MINB resident CTAs need
+      int pct = (int)((MINB * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 5;
+      cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+    }
+    if (getenv("RATILQR_DEBUG")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, THREADS, smem);
+      fprintf(stderr, "[ratilqr] k_ileqg_solve threads=%d minb=%d smem=%zu -> %d resident CTAs/SM\n", THREADS, MINB, smem, nb);
+    }
+  }
+  k_ileqg_solve<D, CT, THREADS, MINB><<<blocks, THREADS, smem, st>>>(P);
 }
 
 // launch shape = (threads per CTA, min resident CTAs per SM => register cap).  The default was chosen from
@@ -51,7 +73,7 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
       case 7: launch_shape<D, CT, 32, 14>(P, st); return;   // 144 regs
       case 8: launch_shape<D, CT, 32, 13>(P, st); return;   // 152 regs
       case 9: launch_shape<D, CT, 32, 10>(P, st); return;   // 200 regs
-      default: launch_shape<D, CT, 32, 12>(P, st); return;
+      default: launch_shape<D, CT, 64, 6>(P, st); return;    // best of the sweep in profiles/r01_tune_*.jsonl
     }
   } else {
     launch_shape<D, CT, 64, 4>(P, st);

@@ -19,10 +19,14 @@ if os.environ.get("TUNE_SORT_THETA"):
     theta = np.sort(theta.reshape(P, -1), axis=1).reshape(-1)
 be.stage(spec, x0, u, theta, P=P)
 be.run(2)
+sampler = bench.ClockSampler(0)
+sampler.start()
 ms = be.run(reps) / reps
+clk = sampler.stop()
 res = be.fetch()
 flops = float(np.sum(bench.algorithmic_flops(res["iters"], res["trials"])))
 print(json.dumps({"shape": shape, "problems": P, "ms": ms, "solves_per_s": theta.size / ms * 1e3,
-                  "tflops": flops / ms / 1e9, "ok": int((res["status"] == 0).sum()), "B": int(theta.size),
+                  "tflops": flops / ms / 1e9, "ok": int((res["status"] == 0).sum()), "B": int(theta.size), "sm_mhz": clk.get("sm_mhz"), "reasons": clk.get("reasons"),
+                  "lib": os.path.basename(os.environ.get("RATILQR_B200_LIB", "default")),
                   "sorted": bool(os.environ.get("TUNE_SORT_THETA")), "iters_minmax": [int(res["iters"].min()), int(res["iters"].max())],
                   "trials_minmax": [int(res["trials"].min()), int(res["trials"].max())]}))

@@ -76,7 +76,9 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
   P.perm = in->K >= 2 ? perm.data() : nullptr;
   const int cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
   int rc = dispatch(desc->model_id, cost_id, [&](auto D, auto CT) {
-    for (size_t b = 0; b < B; ++b) solve_instance<decltype(D), decltype(CT)>(P, b);
+    double stage_area[2 * RL_STAGE_NV];
+    Stage sg; sg.base = stage_area; sg.stride = 1;  // exercises the staged code path on the host
+    for (size_t b = 0; b < B; ++b) solve_instance<decltype(D), decltype(CT)>(P, b, sg);
   });
   if (rc) return rc;
   for (size_t b = 0; b < B; ++b) {
