@@ -141,6 +141,26 @@ int32_t ratilqr_ce_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc,
                          const ratilqr_ileqg_opts* opts, const ratilqr_batch_in* in,
                          double kl_bound, double* cost, int32_t* status);
 
+/* solve!(::CrossEntropyBilevelOptimizationSolver, ...) (cross_entropy_bilevel_optimization.jl:364-415) for a
+ * FLEET of P independent problems advanced in lock-step rounds: per round every still-active problem draws
+ * num_samples positive theta (get_positive_samples :233-246), ONE batched launch solves all P*num_samples
+ * instances, then the feasibility / redraw logic (:291-311), theta_min/max bookkeeping (:314-324) and the
+ * elite refit (:326-334) run per problem on the device.  Final solve with the retry rule of :390-414.
+ * z_inject: P*nz standard normals (row p = the stream rand(rng, Normal) of problem p), or NULL -> Philox(seed).
+ * mu_init / sigma_init: P values, in-out (they persist across solve! calls, :66-68).  Outputs are P long;
+ * `final` (B = P) receives the trajectories / status of the final solve. */
+typedef struct {
+  int32_t num_samples, num_elite, iter_max; double lambda; int32_t use_theta_max;
+} ratilqr_ce_opts;
+int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                               const ratilqr_ce_opts* ce, int32_t P, const double* x0, int32_t x0_count,
+                               const double* u_init, int32_t u_count, double kl_bound,
+                               const double* z_inject, int64_t nz, uint64_t seed,
+                               double* mu_init, double* sigma_init,
+                               double* theta_opt, double* value, double* theta_min, double* theta_max,
+                               double* mu, double* sigma, int64_t* nz_used, int32_t* rounds,
+                               ratilqr_ileqg_out* final);
+
 /* Device-resident variant used for throughput measurement: stage once, run many times.
  * stage = H2D of inputs; run = the solve kernel only, `reps` launches back to back on the
  * ctx stream, bracketed by CUDA events recorded on that stream (ms_total out);

@@ -60,6 +60,11 @@ class GenerativeDesc(C.Structure):  # ratilqr_generative_desc
     ]
 
 
+class CeOpts(C.Structure):  # ratilqr_ce_opts
+    _fields_ = [("num_samples", C.c_int32), ("num_elite", C.c_int32), ("iter_max", C.c_int32), ("lam", C.c_double),
+                ("use_theta_max", C.c_int32)]
+
+
 def _dp(a):
     return None if a is None else a.ctypes.data_as(c_double_p)
 
@@ -156,6 +161,9 @@ class CApi:
         self.f_mc = self._fn("mc_rollout", [vp, PD, i32, dp, dp, dp, i32, dp, C.c_uint64, f64, dp, dp, dp])
         self.f_pets_costs = self._fn("pets_costs", [vp, PD, GD, dp, dp, i32, i32, dp, C.c_uint64, dp])
         self.f_pets_refit = self._fn("pets_refit", [vp, i32, i32, i32, i32, f64, dp, dp, dp, dp, ip])
+        self.f_ce_fleet = self._fn("ce_solve_fleet", [vp, PD, IO, C.POINTER(CeOpts), i32, dp, i32, dp, i32, f64, dp, C.c_int64,
+                                                      C.c_uint64, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int64),
+                                                      ip, OUT])
         self.f_stage = self._fn("ileqg_stage", [vp, PD, IO, BI])
         self.f_run = self._fn("ileqg_run", [vp, i32, C.POINTER(C.c_float)])
         self.f_fetch = self._fn("ileqg_fetch", [vp, OUT])
@@ -223,6 +231,44 @@ class CApi:
                        _dp(res["mu"]), _dp(res["d_current"]), _dp(res.get("eps_hist")), eps_hist_cap)
         d = spec.desc()
         self._check(self.f_solve(self.ctx, C.byref(d), C.byref(opts), C.byref(bi), C.byref(out)), "ileqg_solve_batch")
+        return res
+
+    def ce_solve_fleet(self, spec, x0, u_init, kl_bound, mu_init, sigma_init, num_samples=10, num_elite=3, iter_max=5,
+                       lam=0.5, use_theta_max=False, z_inject=None, seed=0, opts=None, want=("x", "l", "L")):
+        """solve!(::CrossEntropyBilevelOptimizationSolver) for P problems at once (cross_entropy...:364-415).
+        x0 (n, P); mu_init/sigma_init scalars or (P,); z_inject (P, nz) standard normals or None -> Philox(seed)."""
+        opts = opts or make_opts()
+        n, m, N = spec.n, spec.m, spec.N
+        x0 = np.asarray(x0, dtype=np.float64).reshape(n, -1)
+        P = max(x0.shape[1], spec.cost_params_count)
+        u_init = np.asarray(u_init, dtype=np.float64)
+        u_count = 1 if u_init.ndim == 2 else u_init.shape[-1]
+        x0f, uf = _f64(x0), _f64(u_init)
+        mu_i = np.ascontiguousarray(np.broadcast_to(np.asarray(mu_init, np.float64), (P,))).copy()
+        sg_i = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma_init, np.float64), (P,))).copy()
+        zf, nz = None, 0
+        if z_inject is not None:
+            z = np.ascontiguousarray(np.asarray(z_inject, dtype=np.float64).reshape(P, -1))
+            zf, nz = z.reshape(-1), z.shape[1]
+        res = dict(theta_opt=np.zeros(P), value=np.zeros(P), theta_min=np.zeros(P), theta_max=np.zeros(P), mu=np.zeros(P),
+                   sigma=np.zeros(P), nz_used=np.zeros(P, np.int64), status=np.zeros(P, np.int32), iters=np.zeros(P, np.int32))
+        if "x" in want:
+            res["x"] = np.zeros((n, N + 1, P), order="F")
+        if "l" in want:
+            res["l"] = np.zeros((m, N, P), order="F")
+        if "L" in want:
+            res["L"] = np.zeros((m, n, N, P), order="F")
+        out = IleqgOut(_dp(res.get("x")), _dp(res.get("l")), _dp(res.get("L")), None, _ip(res["status"]), _ip(res["iters"]),
+                       None, None, None, None, None, 0)
+        ce = CeOpts(int(num_samples), int(num_elite), int(iter_max), float(lam), int(bool(use_theta_max)))
+        rounds = C.c_int32(0)
+        d = spec.desc()
+        self._check(self.f_ce_fleet(self.ctx, C.byref(d), C.byref(opts), C.byref(ce), P, _dp(x0f), x0.shape[1], _dp(uf), u_count,
+                                    float(kl_bound), _dp(zf), nz, int(seed), _dp(mu_i), _dp(sg_i), _dp(res["theta_opt"]),
+                                    _dp(res["value"]), _dp(res["theta_min"]), _dp(res["theta_max"]), _dp(res["mu"]),
+                                    _dp(res["sigma"]), res["nz_used"].ctypes.data_as(C.POINTER(C.c_int64)), C.byref(rounds),
+                                    C.byref(out)), "ce_solve_fleet")
+        res["mu_init"], res["sigma_init"], res["rounds"] = mu_i, sg_i, int(rounds.value)
         return res
 
     # device-resident variant (throughput measurement): stage once, run many, fetch

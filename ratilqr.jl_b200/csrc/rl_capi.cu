@@ -95,11 +95,11 @@ __global__ void k_ce_cost(int B, const double* value, const int32_t* status, con
 }
 
 static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
-                          const ratilqr_batch_in* in, int eps_cap) {
+                          const ratilqr_batch_in* in, int eps_cap, bool device_theta = false) {
   ctx->staged = false;
   if (const char* m = rlh::check_desc(desc, true)) FAIL(-1, m);
   if (const char* m = check_opts(opts)) FAIL(-3, m);
-  if (!in || in->P < 1 || in->K < 1 || !in->x0 || !in->u_init || !in->theta) FAIL(-1, "bad batch description");
+  if (!in || in->P < 1 || in->K < 1 || !in->x0 || !in->u_init || (!in->theta && !device_theta)) FAIL(-1, "bad batch description");
   if ((in->x0_count != 1 && in->x0_count != in->P) || (in->u_count != 1 && in->u_count != in->P)) FAIL(-1, "x0_count/u_count must be 1 or P");
   if (desc->cost_params_count != 1 && desc->cost_params_count != in->P) FAIL(-1, "cost_params_count must be 1 or P");
   CU(cudaSetDevice(ctx->device));
@@ -114,7 +114,8 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   UP(ctx->d_cp, desc->cost_params, (size_t)desc->n_cost_params * desc->cost_params_count * 8);
   UP(ctx->d_x0, in->x0, (size_t)n * in->x0_count * 8);
   UP(ctx->d_u, in->u_init, (size_t)m * N * in->u_count * 8);
-  UP(ctx->d_theta, in->theta, B * 8);
+  if (device_theta) CU(ctx->d_theta.reserve(B * 8));  // theta is produced on the device (fleet CE)
+  else UP(ctx->d_theta, in->theta, B * 8);
   CU(ctx->d_X.reserve(2 * (size_t)(N + 1) * n * B * 8));
   CU(ctx->d_U.reserve(2 * (size_t)N * m * B * 8));
   CU(ctx->d_Lg.reserve((size_t)N * m * n * B * 8));
@@ -152,7 +153,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   { const char* e = getenv("RATILQR_NO_STAGE"); P.use_stage = (e && e[0] == '1') ? 0 : 1; }
   // warp-homogeneous scheduling: lanes of a warp get neighbouring theta of one problem
   CU(ctx->d_perm.reserve(B * 4));
-  if (rll::launch_sort_theta(P.theta, in->P, in->K, ctx->d_perm.as<int32_t>(), ctx->stream) == 0) {
+  if (!device_theta && rll::launch_sort_theta(P.theta, in->P, in->K, ctx->d_perm.as<int32_t>(), ctx->stream) == 0) {
     if (int rc = check_launch(ctx, "k_sort_theta")) return rc;
     P.perm = ctx->d_perm.as<int32_t>();
   } else {
@@ -596,6 +597,110 @@ int32_t ratilqr_pets_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, c
   DOWNSYNC(mu, ctx->s[3].p, m * N * 8); DOWNSYNC(Sigma, ctx->s[4].p, m * m * N * 8);
   CU(cudaStreamSynchronize(ctx->stream));
   if (err) FAIL(-4, "a Sigma_t is not positive definite (PosDefException in MvNormal, pets.jl:212)");
+  return 0;
+}
+
+// ---- RAT iLQR for a fleet of problems (cross_entropy_bilevel_optimization.jl:364-415) ------------------------
+int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                               const ratilqr_ce_opts* ce, int32_t P, const double* x0, int32_t x0_count,
+                               const double* u_init, int32_t u_count, double kl_bound, const double* z_inject,
+                               int64_t nz, uint64_t seed, double* mu_init, double* sigma_init, double* theta_opt,
+                               double* value, double* theta_min, double* theta_max, double* mu, double* sigma,
+                               int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out) {
+  if (!ctx) return -1;
+  if (!ce || P < 1 || !mu_init || !sigma_init || !theta_opt || !value) FAIL(-1, "bad arguments");
+  if (!(kl_bound >= 0)) FAIL(-3, "KL Divergence Bound must be non-negative");  // :368
+  if (ce->num_samples < 1 || ce->num_elite < 1 || ce->num_elite > ce->num_samples || ce->iter_max < 1) FAIL(-3, "bad CE options");
+  const int S = ce->num_samples;
+  cudaStream_t st = ctx->stream;
+  // per-problem CE state on the device (scratch slots s[0..12] are free during a solve)
+  rll::CeFleet c;
+  memset(&c, 0, sizeof(c));
+  c.P = P; c.S = S; c.num_elite = ce->num_elite; c.iter_max = ce->iter_max; c.use_theta_max = ce->use_theta_max;
+  c.lambda = ce->lambda; c.kl = kl_bound; c.nz = nz; c.seed = seed;
+  ratilqr_batch_in in;
+  in.P = P; in.K = S; in.x0 = x0; in.x0_count = x0_count; in.u_init = u_init; in.u_count = u_count; in.theta = nullptr;
+  int rc = 0, rounds = 0;
+  const size_t Pb = (size_t)P * 8;
+  std::vector<double> init_tmin(P, HUGE_VAL), zeros(P, 0.0);
+  std::vector<int32_t> ones(P, 1), izeros(P, 0);
+  std::vector<long long> lzeros(P, 0);
+  if (kl_bound > 0) {
+    if ((rc = stage_internal(ctx, desc, opts, &in, 0, true))) return rc;
+    UP(ctx->s[0], mu_init, Pb); UP(ctx->s[1], sigma_init, Pb);
+    UP(ctx->s[2], mu_init, Pb); UP(ctx->s[3], sigma_init, Pb);          // initialize! :133-138: mu, sigma <- *_init
+    UP(ctx->s[4], init_tmin.data(), Pb); UP(ctx->s[5], zeros.data(), Pb);  // theta_min = Inf, theta_max = 0
+    CU(ctx->s[6].reserve(Pb)); CU(ctx->s[7].reserve(Pb));
+    UP(ctx->s[8], lzeros.data(), Pb); UP(ctx->s[9], ones.data(), (size_t)P * 4);  // cursor = 0 ; iter = 1
+    UP(ctx->s[10], ones.data(), (size_t)P * 4); UP(ctx->s[11], izeros.data(), (size_t)P * 4);  // active ; err
+    CU(ctx->s[12].reserve(8));
+    if (z_inject) { UP(ctx->s[13], z_inject, (size_t)P * nz * 8); c.z = ctx->s[13].as<double>(); }
+  } else {
+    in.K = 1;
+    UP(ctx->s[2], mu_init, Pb); UP(ctx->s[3], sigma_init, Pb);
+    UP(ctx->s[0], mu_init, Pb); UP(ctx->s[1], sigma_init, Pb);
+    UP(ctx->s[4], zeros.data(), Pb); UP(ctx->s[5], zeros.data(), Pb);
+    CU(ctx->s[6].reserve(Pb)); CU(ctx->s[7].reserve(Pb));
+    UP(ctx->s[8], lzeros.data(), Pb); UP(ctx->s[9], ones.data(), (size_t)P * 4);
+    UP(ctx->s[10], ones.data(), (size_t)P * 4); UP(ctx->s[11], izeros.data(), (size_t)P * 4);
+    CU(ctx->s[12].reserve(8));
+  }
+  c.mu_init = ctx->s[0].as<double>(); c.sigma_init = ctx->s[1].as<double>(); c.mu = ctx->s[2].as<double>();
+  c.sigma = ctx->s[3].as<double>(); c.theta_min = ctx->s[4].as<double>(); c.theta_max = ctx->s[5].as<double>();
+  c.theta_opt = ctx->s[6].as<double>(); c.value_out = ctx->s[7].as<double>(); c.cursor = ctx->s[8].as<long long>();
+  c.iter = ctx->s[9].as<int32_t>(); c.active = ctx->s[10].as<int32_t>(); c.err = ctx->s[11].as<int32_t>();
+  c.n_active = ctx->s[12].as<int32_t>();
+  if (kl_bound > 0) {
+    c.theta = ctx->d_theta.as<double>(); c.value = ctx->sp.value; c.status = ctx->sp.status;
+    ctx->sp.active = c.active;
+    while (true) {  // one round = draw -> batched solve -> per-problem CE logic; one host sync per round
+      rll::launch_ce_draw(c, st);
+      if ((rc = check_launch(ctx, "k_ce_draw"))) return rc;
+      if ((rc = run_internal(ctx, 1, nullptr))) return rc;
+      CU(cudaMemsetAsync(c.n_active, 0, 4, st));
+      rll::launch_ce_update(c, st);
+      if ((rc = check_launch(ctx, "k_ce_update"))) return rc;
+      int32_t n_active = 0;
+      CU(cudaMemcpyAsync(&n_active, c.n_active, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      rounds++;
+      if (n_active == 0) break;
+      if (rounds > 100000) FAIL(-6, "CE redraw loop does not terminate (the reference would spin forever here)");
+    }
+  }
+  // final solve at theta_opt with the retry rule (:390-414); B = P instances, theta on the device
+  in.K = 1;
+  if ((rc = stage_internal(ctx, desc, opts, &in, final_out && final_out->eps_hist ? final_out->eps_hist_cap : 0, true))) return rc;
+  rll::launch_ce_pick_theta(c, ctx->d_theta.as<double>(), st);
+  if ((rc = check_launch(ctx, "k_ce_pick_theta"))) return rc;
+  ctx->sp.active = c.active;
+  int final_rounds = 0;
+  while (true) {
+    if ((rc = run_internal(ctx, 1, nullptr))) return rc;
+    CU(cudaMemsetAsync(c.n_active, 0, 4, st));
+    rll::launch_ce_final_update(c, ctx->d_theta.as<double>(), ctx->sp.value, ctx->sp.status, st);
+    if ((rc = check_launch(ctx, "k_ce_final_update"))) return rc;
+    int32_t n_active = 0;
+    CU(cudaMemcpyAsync(&n_active, c.n_active, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_active == 0) break;
+    if (++final_rounds > 10000) FAIL(-6, "final solve retry loop does not terminate");
+  }
+  ctx->sp.active = nullptr;
+  DOWNSYNC(theta_opt, c.theta_opt, Pb); DOWNSYNC(value, c.value_out, Pb);
+  DOWNSYNC(mu_init, c.mu_init, Pb); DOWNSYNC(sigma_init, c.sigma_init, Pb);
+  DOWNSYNC(mu, c.mu, Pb); DOWNSYNC(sigma, c.sigma, Pb);
+  if (kl_bound > 0) { DOWNSYNC(theta_min, c.theta_min, Pb); DOWNSYNC(theta_max, c.theta_max, Pb); }
+  std::vector<long long> cur(P);
+  std::vector<int32_t> err(P);
+  CU(cudaMemcpyAsync(cur.data(), c.cursor, Pb, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(err.data(), c.err, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (kl_bound <= 0) { for (int p = 0; p < P; ++p) { if (theta_min) theta_min[p] = 0.0; if (theta_max) theta_max[p] = 0.0; } }  // :408
+  if (nz_used) for (int p = 0; p < P; ++p) nz_used[p] = cur[p];
+  if (rounds_out) *rounds_out = rounds;
+  for (int p = 0; p < P; ++p) if (err[p] == 1) FAIL(-5, "a problem exhausted its injected normal stream (or needed > 1e6 draws)");
+  if (final_out) return fetch_internal(ctx, final_out);
   return 0;
 }
 

@@ -346,4 +346,110 @@ void launch_pets_refit(int m, int N, int C, int num_elite, double smoothing, con
   k_pets_refit<<<RL_BLOCKS(N * m, 64), 64, 0, st>>>(m, N, num_elite, smoothing, controls, elite_idx, mu, Sigma);
 }
 
+
+// ---- RAT iLQR fleet kernels: thread = problem (the per-problem logic is sequential and tiny) ---------------
+// get_positive_samples (cross_entropy_bilevel_optimization.jl:233-246): sequential rejection sampling
+__global__ void k_ce_draw(CeFleet c) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= c.P || !c.active[p]) return;
+  const bool first = c.iter[p] == 1;                       // :266-279
+  const double mm = first ? c.mu_init[p] : c.mu[p], ss = first ? c.sigma_init[p] : c.sigma[p];
+  long long cur = c.cursor[p];
+  int cnt = 0;
+  long long guard = 0;
+  while (cnt < c.S) {
+    if ((c.z && cur >= c.nz) || ++guard > 1000000) { c.err[p] = 1; c.active[p] = 0; break; }
+    double z0, z1;
+    if (c.z) z0 = c.z[(size_t)p * c.nz + cur];
+    else rl::philox_normal2(c.seed, (uint64_t)p, (uint32_t)cur, (uint32_t)(cur >> 32), &z0, &z1);
+    cur++;
+    double t = mm + ss * z0;                                // rand(rng, Normal(mu, sigma))
+    if (t > 0.0) c.theta[(size_t)p * c.S + cnt++] = t;
+  }
+  c.cursor[p] = cur;
+}
+
+// feasibility logic, theta_min/max bookkeeping, stable sort, elite refit (step! :291-334)
+__global__ void k_ce_update(CeFleet c) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= c.P || !c.active[p]) return;
+  const int S = c.S;
+  const double* th = c.theta + (size_t)p * S;
+  const double* val = c.value + (size_t)p * S;
+  const int32_t* st = c.status + (size_t)p * S;
+  auto cost = [&](int i) { return st[i] == 0 ? val[i] + c.kl / th[i] : HUGE_VAL; };  // :193, exceptions -> Inf
+  int num_inf = 0;
+  for (int i = 0; i < S; ++i) { double ci = cost(i); num_inf += (ci == HUGE_VAL || ci == -HUGE_VAL) ? 1 : 0; }
+  const int num_valid = S - num_inf;
+  const double thr = fmax((double)c.num_elite, S * c.lambda);
+  const bool first = c.iter[p] == 1;
+  if (first && num_valid < thr) { c.mu_init[p] *= c.lambda; c.sigma_init[p] *= c.lambda; atomicAdd(c.n_active, 1); return; }  // :293-298 redraw
+  else if (first && num_valid == S) { c.mu_init[p] /= c.lambda; c.sigma_init[p] /= c.lambda; }                                 // :299-305
+  else if (!(num_valid >= thr)) { atomicAdd(c.n_active, 1); return; }                                                         // redraw, unchanged mu/sigma
+  double tmin = c.theta_min[p], tmax = c.theta_max[p];
+  for (int i = 0; i < S; ++i) {  // :314-324 (if / elseif quirk kept)
+    double ci = cost(i);
+    if (ci == HUGE_VAL || ci == -HUGE_VAL) continue;
+    if (th[i] < tmin) tmin = th[i];
+    else if (th[i] > tmax) tmax = th[i];
+  }
+  c.theta_min[p] = tmin; c.theta_max[p] = tmax;
+  // elites = first num_elite of the stable ascending sort by cost (NaN last): selection by rank
+  double sum = 0.0;
+  for (int e = 0; e < c.num_elite; ++e) {
+    for (int i = 0; i < S; ++i) {
+      double ci = cost(i);
+      int rank = 0;
+      for (int j = 0; j < S; ++j) rank += key_less(cost(j), j, ci, i) ? 1 : 0;
+      if (rank == e) { sum += th[i]; break; }
+    }
+  }
+  const double mu_new = sum / c.num_elite;  // :329
+  double ss = 0.0;
+  for (int e = 0; e < c.num_elite; ++e) {
+    for (int i = 0; i < S; ++i) {
+      double ci = cost(i);
+      int rank = 0;
+      for (int j = 0; j < S; ++j) rank += key_less(cost(j), j, ci, i) ? 1 : 0;
+      if (rank == e) { ss += (th[i] - mu_new) * (th[i] - mu_new); break; }
+    }
+  }
+  c.mu[p] = mu_new;
+  c.sigma[p] = sqrt(ss / c.num_elite);  // :330 population std
+  if (c.iter[p] >= c.iter_max) c.active[p] = 0;   // CE finished for this problem
+  else { c.iter[p] += 1; atomicAdd(c.n_active, 1); }
+}
+
+__global__ void k_ce_pick_theta(CeFleet c, double* theta_final) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= c.P) return;
+  double t = c.kl > 0 ? (c.use_theta_max ? c.theta_max[p] : c.mu[p]) : 0.0;  // :374-389
+  theta_final[p] = t;
+  c.theta_opt[p] = t;
+  c.active[p] = c.err[p] ? 0 : 1;
+}
+
+// final solve bookkeeping: success -> value (+ kl/theta); failure -> theta_opt = max(0, theta_opt - sigma), retry (:405-413)
+__global__ void k_ce_final_update(CeFleet c, double* theta_final, const double* value, const int32_t* status) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= c.P || !c.active[p]) return;
+  if (status[p] == 0) {
+    c.value_out[p] = c.kl > 0 ? value[p] + c.kl / theta_final[p] : value[p];
+    c.theta_opt[p] = theta_final[p];
+    c.active[p] = 0;
+  } else {
+    double t = fmax(0.0, theta_final[p] - c.sigma[p]);
+    if (t == theta_final[p] && t == 0.0) { c.err[p] = 2; c.active[p] = 0; c.value_out[p] = HUGE_VAL; return; }  // even iLQG failed
+    theta_final[p] = t;
+    atomicAdd(c.n_active, 1);
+  }
+}
+
+void launch_ce_draw(const CeFleet& c, cudaStream_t st) { k_ce_draw<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c); }
+void launch_ce_update(const CeFleet& c, cudaStream_t st) { k_ce_update<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c); }
+void launch_ce_pick_theta(const CeFleet& c, double* tf, cudaStream_t st) { k_ce_pick_theta<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c, tf); }
+void launch_ce_final_update(const CeFleet& c, double* tf, const double* v, const int32_t* s, cudaStream_t st) {
+  k_ce_final_update<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c, tf, v, s);
+}
+
 }  // namespace rll

@@ -81,6 +81,22 @@ void launch_pets_refit(int m, int N, int C, int num_elite, double smoothing, con
                        const double* cost, double* mu, double* Sigma, int32_t* elite_idx, int32_t* sort_ws,
                        cudaStream_t st);
 
+// ---- RAT iLQR (CE over theta) for a fleet: per-problem state lives on the device ------------------------
+struct CeFleet {
+  int P, S, num_elite, iter_max, use_theta_max;
+  double lambda, kl;
+  const double* z; long long nz; unsigned long long seed;   // injected normals (P*nz) or Philox
+  double *mu_init, *sigma_init, *mu, *sigma, *theta_min, *theta_max, *theta_opt, *value_out;
+  long long* cursor; int32_t *iter, *active, *err;
+  double* theta;            // P*S draws (device), consumed by the solve kernel
+  const double* value; const int32_t* status;   // results of the batched solve (P*S)
+  int32_t* n_active;        // single counter
+};
+void launch_ce_draw(const CeFleet& c, cudaStream_t st);
+void launch_ce_update(const CeFleet& c, cudaStream_t st);
+void launch_ce_pick_theta(const CeFleet& c, double* theta_final, cudaStream_t st);
+void launch_ce_final_update(const CeFleet& c, double* theta_final, const double* value, const int32_t* status, cudaStream_t st);
+
 // DFMA throughput probe: returns total flops issued
 double launch_fp64_probe(double* sink, int iters, cudaStream_t st);
 

@@ -149,3 +149,41 @@ def test_nm_whole_solve_matches_oracle_restatement(backend, oracle_be):
            C.byref(th), C.byref(val), C.byref(it), C.byref(ev), x.ctypes.data_as(dp), l.ctypes.data_as(dp),
            L.ctypes.data_as(dp), C.byref(st))
     assert np.isclose(got2[0], th.value, rtol=1e-12) and np.isclose(got2[4], val.value, rtol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kl,mu0,sg0", [(1.0, 60.0, 30.0), (1.0, 600.0, 300.0), (0.0, 60.0, 30.0)])
+def test_ce_fleet_on_device_matches_oracle_per_problem(gpu_be, oracle_be, kl, mu0, sg0):
+    """ratilqr_ce_solve_fleet (whole RAT iLQR loop on the device, P problems in lock-step) vs P independent runs of the
+    oracle's restatement of solve! with the same injected normal streams."""
+    P = 6
+    prob, cps, x0, u = wl.fleet(P, N=20)
+    spec = prob.spec(cost_params=cps)
+    z = np.random.Generator(np.random.Philox(key=17)).standard_normal((P, 3000))
+    # (600, 300): most first draws are infeasible => per-problem shrink / redraw rounds of different lengths
+    g = gpu_be.ce_solve_fleet(spec, x0, u, kl, mu0, sg0, num_samples=8, num_elite=3, iter_max=3, z_inject=z)
+    f = oracle_be.raw.oracle_ce_solve
+    f.restype = C.c_int32
+    n, m, N = spec.n, spec.m, spec.N
+    opts = make_opts()
+    uflat = np.ascontiguousarray(u.ravel(order="F"))
+    for p in range(P):
+        sp = prob.spec(cost_params=cps[p])
+        d = sp.desc()
+        ce = OracleCEOpts(mu0, sg0, 8, 3, 3, 0.5, 0)
+        outs = [C.c_double() for _ in range(6)]
+        nz, st = C.c_int64(), C.c_int32()
+        x = np.zeros((n, N + 1), order="F"); l = np.zeros((m, N), order="F"); L = np.zeros((m, n, N), order="F")
+        x0p = np.ascontiguousarray(x0[:, p])
+        rc = f(C.byref(d), C.byref(opts), C.byref(ce), x0p.ctypes.data_as(dp), uflat.ctypes.data_as(dp), C.c_double(kl),
+               z[p].ctypes.data_as(dp), C.c_int64(z.shape[1]), *[C.byref(o) for o in outs], C.byref(nz),
+               x.ctypes.data_as(dp), l.ctypes.data_as(dp), L.ctypes.data_as(dp), C.byref(st))
+        assert rc == 0 and st.value == 0
+        theta_opt, value, th_min, th_max, mu, sigma = [o.value for o in outs]
+        assert g["nz_used"][p] == nz.value, p            # same draw / redraw history
+        assert np.isclose(g["theta_opt"][p], theta_opt, rtol=1e-9) and np.isclose(g["value"][p], value, rtol=1e-9)
+        assert np.isclose(g["theta_min"][p], th_min, rtol=1e-12) and np.isclose(g["theta_max"][p], th_max, rtol=1e-12)
+        assert np.isclose(g["mu_init"][p], ce.mu_init) and np.isclose(g["sigma_init"][p], ce.sigma_init)
+        if kl > 0:
+            assert np.isclose(g["mu"][p], mu, rtol=1e-9) and np.isclose(g["sigma"][p], sigma, rtol=1e-9)
+        assert np.allclose(g["x"][..., p], x, rtol=1e-9, atol=1e-12) and np.allclose(g["L"][..., p], L, rtol=1e-9, atol=1e-12)
