@@ -40,6 +40,9 @@ struct ratilqr_ctx {
   // staged solve
   bool staged = false;
   int model_id = 0, cost_id = 0, n = 0, m = 0, N = 0, B = 0, eps_cap = 0;
+  bool coop = false;          // staged solve runs on the warp-cooperative kernel
+  int coop_cost_id = 0;
+  DBuf d_coop_traj;
   rl::SolveParams sp;
   DBuf d_cp, d_W, d_Winv, d_detW, d_x0, d_u, d_theta, d_X, d_U, d_Lg, d_DL;
   DBuf d_value, d_status, d_iters, d_trials, d_restarts, d_mu, d_d, d_cur, d_eps, d_perm;
@@ -163,6 +166,33 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   // structure-specialised kernel when the quadratic cost is diagonal (bit-identical results, fewer flops)
   ctx->cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
   ctx->n = n; ctx->m = m; ctx->N = N; ctx->B = (int)B; ctx->eps_cap = eps_cap;
+  // kernel choice: the warp-cooperative kernel when the per-stage state is too big for one thread's registers
+  // (n > 6: the quadrotor); one thread per instance otherwise.  (For n = 4 the ~20 synchronised shared-memory
+  // phases per stage cost more than they save: 44 ms vs 21 ms for 1024 unicycle solves, profiles/r01_coop_*.)
+  ctx->coop = false;
+  ctx->coop_cost_id = rlh::quad_is_diag(desc) ? RL_COST_QUAD_DIAG : desc->cost_id;
+  if (desc->model_id == RATILQR_MODEL_POWER_LAW) ctx->coop_cost_id = desc->cost_id;
+  size_t csm = 0;
+  if (rll::coop_smem_query(desc->model_id, ctx->coop_cost_id, N, &csm) == 0) {
+    size_t per_sm = (227 * 1024) / (csm + 1024);
+    if (per_sm > 32) per_sm = 32;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const size_t capacity = per_sm * (size_t)sms;
+    const char* e = getenv("RATILQR_COOP");  // 1 = force, 0 = never (tuning / A-B runs)
+    (void)capacity;
+    ctx->coop = e ? (e[0] == '1') : (n > 6);
+  }
+  if (ctx->coop) {
+    P.perm = nullptr;
+    CU(ctx->d_out1.reserve((size_t)n * (N + 1) * B * 8));
+    CU(ctx->d_out2.reserve((size_t)m * N * B * 8));
+    CU(ctx->d_out3.reserve((size_t)m * n * N * B * 8));
+    P.xo = ctx->d_out1.as<double>(); P.lo = ctx->d_out2.as<double>(); P.Lo = ctx->d_out3.as<double>();
+    CU(cudaMemsetAsync(P.Lo, 0, (size_t)m * n * N * B * 8, ctx->stream));
+    if (csm > 200 * 1024 || csm == 0) {}  // (trajectories in shared memory)
+    CU(ctx->d_coop_traj.reserve(rl::coop_traj_doubles(n, m, N) * B * 8));
+  }
   ctx->staged = true;
   return 0;
 }
@@ -173,6 +203,11 @@ static int run_internal(ratilqr_ctx* ctx, int reps, float* ms_total) {
   CU(cudaSetDevice(ctx->device));
   if (ms_total) CU(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int r = 0; r < reps; ++r) {
+    if (ctx->coop) {
+      if (rll::launch_solve_coop(ctx->model_id, ctx->coop_cost_id, ctx->sp, ctx->d_coop_traj.as<double>(), ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
+      if (int rc = check_launch(ctx, "k_ileqg_solve_coop")) return rc;
+      continue;
+    }
     if (rll::launch_solve(ctx->model_id, ctx->cost_id, ctx->sp, ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
     if (int rc = check_launch(ctx, "k_ileqg_solve")) return rc;
   }
@@ -195,7 +230,9 @@ static int fetch_internal(ratilqr_ctx* ctx, ratilqr_ileqg_out* out) {
   if (out->x) { CU(ctx->d_out1.reserve((size_t)n * (N + 1) * B * 8)); dx = ctx->d_out1.as<double>(); }
   if (out->l) { CU(ctx->d_out2.reserve((size_t)m * N * B * 8)); dl = ctx->d_out2.as<double>(); }
   if (out->L) { CU(ctx->d_out3.reserve((size_t)m * n * N * B * 8)); dL = ctx->d_out3.as<double>(); }
-  if (dx || dl || dL) {
+  if (ctx->coop) {  // the cooperative kernel already wrote x, l, L in host layout
+    dx = out->x ? ctx->sp.xo : nullptr; dl = out->l ? ctx->sp.lo : nullptr; dL = out->L ? ctx->sp.Lo : nullptr;
+  } else if (dx || dl || dL) {
     rll::launch_gather(n, m, N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.cur, ctx->sp.perm, dx, dl, dL, st);
     if (int rc = check_launch(ctx, "k_gather", (dx ? 1 : 0) + (dl ? 1 : 0) + (dL ? 1 : 0))) return rc;
   }
@@ -259,7 +296,7 @@ int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
   DBuf* all[] = {&ctx->d_cp, &ctx->d_W, &ctx->d_Winv, &ctx->d_detW, &ctx->d_x0, &ctx->d_u, &ctx->d_theta, &ctx->d_X,
                  &ctx->d_U, &ctx->d_Lg, &ctx->d_DL, &ctx->d_value, &ctx->d_status, &ctx->d_iters, &ctx->d_trials,
                  &ctx->d_restarts, &ctx->d_mu, &ctx->d_d, &ctx->d_cur, &ctx->d_eps, &ctx->d_perm, &ctx->d_out1, &ctx->d_out2,
-                 &ctx->d_out3, &ctx->d_cost};
+                 &ctx->d_out3, &ctx->d_cost, &ctx->d_coop_traj};
   for (DBuf* b : all) b->release();
   for (DBuf& b : ctx->s) b.release();
   cudaEventDestroy(ctx->ev0);

@@ -1,0 +1,459 @@
+// rl_coop.cuh -- warp-cooperative iLEQG solve: ONE WARP per instance.
+//
+// The thread-per-instance kernel (rl_core.cuh) is throughput-optimal for fleets but its latency is that of
+// one serial thread, and at n = 12 its per-thread matrices spill to strided local memory.  Small batches
+// (a single MPC problem: <= 10 theta; Nelder-Mead: <= 6 candidates) and the quadrotor need intra-instance
+// parallelism instead: here the per-stage matrices AND the instance's trajectories live in shared memory and
+// the OUTPUT elements of every small dense operation are spread over the 32 lanes.  Each output is still
+// accumulated by one lane in the canonical order, so results are bit-identical to the serial formulation.
+//
+// Code is written as a sequence of `phase`s: on the device every lane runs the phase body once and the warp
+// synchronises; the g++ test build (tests/_hostemu) runs the 32 virtual lanes of each phase one after another.
+// All control flow is warp-uniform (decisions are taken on values every lane reads from shared memory).
+#pragma once
+#include "rl_core.cuh"
+
+namespace rl {
+
+template <class F>
+RL_HD void phase(int lane, F&& f) {
+#if defined(__CUDA_ARCH__)
+  f(lane);
+  __syncwarp();
+#else
+  (void)lane;
+  for (int l = 0; l < 32; ++l) f(l);
+#endif
+}
+
+// shared-memory workspace of one warp (doubles)
+template <int n, int m>
+struct CoopWs {
+  double S[n * n], sv[n], M[n * n], invd[n], Z[n * n], z[n], DS[n * n], Dsv[n];
+  double A[n * n], B[n * m], Q[n * n], R[m * m], Pm[m * n], qv[n], r[m];
+  double T[n * n], U[n * m], g[m], G[m * n], H[m * m], CH[m * m], invh[m], L[m * n], dl[m], HL[m * n], Hdl[m];
+  double x[n], u[m], xn[n], Sn[n * n], svn[n];
+  double q, flag, nrm;  // stage cost value; domain-error flag; ||l - u||^2 of the rollout step
+};
+
+// per-instance trajectories, contiguous per instance: X[2][(N+1)*n], U[2][N*m], Lg[N*m*n], DL[N*m]
+struct CoopTraj {
+  double *X, *U, *Lg, *DL;
+};
+
+// models whose Jacobian comes from duals evaluate one seeded direction per lane
+template <class D> struct CoopJac {
+  template <int n, int m>
+  RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w) {
+    phase(lane, [&](int l) { if (l == 1) D::jac(mp, w.x, w.u, w.A, w.B); });
+  }
+};
+template <class Body, int n, int m>
+RL_HD void coop_dual_jac(int lane, Body body, const double* mp, CoopWs<n, m>& w) {
+  phase(lane, [&](int l) {
+    if (l >= n + m) return;
+    Dual<1> xd[n], ud[m], xo[n];
+    for (int i = 0; i < n; ++i) { xd[i].v = w.x[i]; xd[i].d[0] = (i == l) ? 1.0 : 0.0; }
+    for (int j = 0; j < m; ++j) { ud[j].v = w.u[j]; ud[j].d[0] = (n + j == l) ? 1.0 : 0.0; }
+    body(mp, xd, ud, xo);
+    for (int i = 0; i < n; ++i) { if (l < n) w.A[i + l * n] = xo[i].d[0]; else w.B[i + (l - n) * n] = xo[i].d[0]; }
+  });
+}
+template <> struct CoopJac<Dyn<RATILQR_MODEL_CARTPOLE>> {
+  template <int n, int m> RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w) { coop_dual_jac(lane, CartpoleBody(), mp, w); }
+};
+template <> struct CoopJac<Dyn<RATILQR_MODEL_QUADROTOR>> {
+  template <int n, int m> RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w) { coop_dual_jac(lane, QuadrotorBody(), mp, w); }
+};
+
+// One Riccati stage, cooperative.  w.S / w.sv / s hold (S+, s_vec+, s+) on entry, the stage's values on exit.
+// returns 0 / 1 (M not PD) / 2 (H not PD); identical arithmetic per output element to rl::riccati_stage.
+template <class Tr, bool OPT, bool HAS_DL>
+RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, double mu, const double* RL_RESTRICT W,
+                             const double* RL_RESTRICT Winv, double detW, double& s) {
+  constexpr int n = Tr::n, m = Tr::m;
+  double extra = 0.0;
+  if (theta == 0.0) {
+    phase(lane, [&](int l) {
+      for (int e = l; e < n * n; e += 32) w.DS[e] = w.S[e];
+      for (int e = l; e < n; e += 32) w.Dsv[e] = w.sv[e];
+    });
+    double tr = 0.0;  // every lane redundantly: 1/2 tr(W S+)
+    for (int i = 0; i < n; ++i) {
+      double t = W[i] * w.S[i * n];
+      for (int k = 1; k < n; ++k) t = rl_fma(W[i + k * n], w.S[k + i * n], t);
+      tr = (i == 0) ? t : tr + t;
+    }
+    extra = 0.5 * tr;
+  } else {
+    phase(lane, [&](int l) { for (int e = l; e < n * n; e += 32) w.M[e] = Winv[e] - theta * w.S[e]; });
+    // Cholesky in place, one column per step: lane i owns row i; the pivot is recomputed by every lane
+    double detM = 1.0;
+    int bad = 0;
+    for (int j = 0; j < n; ++j) {
+      double d = w.M[j + j * n];
+      for (int k = 0; k < j; ++k) d = rl_fma(-w.M[j + k * n], w.M[j + k * n], d);
+      if (!(d > 0.0)) { bad = 1; break; }
+      detM = (j == 0) ? d : detM * d;
+      const double inv = rl_rsqrt(d);
+      phase(lane, [&](int l) {
+        if (l == 0) w.invd[j] = inv;
+        for (int i = j + 1 + l; i < n; i += 32) {
+          double a = w.M[j + i * n];
+          for (int k = 0; k < j; ++k) a = rl_fma(-w.M[i + k * n], w.M[j + k * n], a);
+          w.M[i + j * n] = a * inv;
+        }
+      });
+    }
+    if (bad) return 1;
+    // forward substitutions: lane c owns column c of Z = C^-1 S+, one more lane owns z = C^-1 s_vec+
+    phase(lane, [&](int l) {
+      for (int c = l; c <= n; c += 32) {
+        for (int i = 0; i < n; ++i) {
+          double a = (c < n) ? w.S[i + c * n] : w.sv[i];
+          for (int k = 0; k < i; ++k) a = rl_fma(-w.M[i + k * n], (c < n) ? w.Z[k + c * n] : w.z[k], a);
+          if (c < n) w.Z[i + c * n] = a * w.invd[i]; else w.z[i] = a * w.invd[i];
+        }
+      }
+    });
+    phase(lane, [&](int l) {
+      for (int e = l; e < n * n; e += 32) {  // D S+ = S+ + theta Z'Z, upper triangle mirrored
+        int i = e % n, j = e / n;
+        if (j < i) continue;
+        double v = w.Z[i * n] * w.Z[j * n];
+        for (int k = 1; k < n; ++k) v = rl_fma(w.Z[k + i * n], w.Z[k + j * n], v);
+        v = rl_fma(theta, v, w.S[i + j * n]);
+        w.DS[i + j * n] = v;
+        w.DS[j + i * n] = v;
+      }
+      for (int i = l; i < n; i += 32) {
+        double v = w.Z[i * n] * w.z[0];
+        for (int k = 1; k < n; ++k) v = rl_fma(w.Z[k + i * n], w.z[k], v);
+        w.Dsv[i] = rl_fma(theta, v, w.sv[i]);
+      }
+    });
+    double quad = w.z[0] * w.z[0];
+    for (int k = 1; k < n; ++k) quad = rl_fma(w.z[k], w.z[k], quad);
+    extra = (theta / 2) * quad - (1 / (2 * theta)) * log(detW * detM);
+  }
+  phase(lane, [&](int l) {  // T = (D S+) A, U = (D S+) B
+    for (int e = l; e < n * n + n * m; e += 32) {
+      if (e < n * n) { int i = e % n, j = e / n; w.T[e] = coldot<Tr, KindA, n>(w.A, j, w.DS + i, n); }
+      else { int f = e - n * n, i = f % n, j = f / n; w.U[f] = coldot<Tr, KindB, n>(w.B, j, w.DS + i, n); }
+    }
+  });
+  phase(lane, [&](int l) {  // g, G, H (upper mirrored)
+    for (int e = l; e < m + m * n + m * m; e += 32) {
+      if (e < m) w.g[e] = w.r[e] + coldot<Tr, KindB, n>(w.B, e, w.Dsv, 1);
+      else if (e < m + m * n) {
+        int f = e - m, i = f % m, j = f / m;
+        double a = coldot<Tr, KindB, n>(w.B, i, w.T + j * n, 1);
+        w.G[f] = (Tr::p_kind(i, j) == 0) ? a : w.Pm[f] + a;
+      } else {
+        int f = e - m - m * n, i = f % m, j = f / m;
+        if (j < i) continue;
+        double a = coldot<Tr, KindB, n>(w.B, i, w.U + j * n, 1);
+        double h = (Tr::r_kind(i, j) == 0) ? a : w.R[i + j * m] + a;
+        if (i == j) h = h + mu;
+        w.H[i + j * m] = h;
+        w.H[j + i * m] = h;
+      }
+    }
+  });
+  if (OPT) {
+    int bad = 0;
+    for (int j = 0; j < m; ++j) {  // Cholesky of H, same column scheme
+      double d = w.H[j + j * m];
+      for (int k = 0; k < j; ++k) d = rl_fma(-w.CH[j + k * m], w.CH[j + k * m], d);
+      if (!(d > 0.0)) { bad = 1; break; }
+      const double inv = rl_rsqrt(d);
+      phase(lane, [&](int l) {
+        if (l == 0) w.invh[j] = inv;
+        for (int i = j + 1 + l; i < m; i += 32) {
+          double a = w.H[j + i * m];
+          for (int k = 0; k < j; ++k) a = rl_fma(-w.CH[i + k * m], w.CH[j + k * m], a);
+          w.CH[i + j * m] = a * inv;
+        }
+      });
+    }
+    if (bad) return 2;
+    phase(lane, [&](int l) {  // L = -H\G (column c per lane), dl = -H\g (column n)
+      for (int c = l; c <= n; c += 32) {
+        double y[m];
+        for (int i = 0; i < m; ++i) {
+          double a = (c < n) ? w.G[i + c * m] : w.g[i];
+          for (int k = 0; k < i; ++k) a = rl_fma(-w.CH[i + k * m], y[k], a);
+          y[i] = a * w.invh[i];
+        }
+        for (int i = m - 1; i >= 0; --i) {
+          double a = y[i];
+          for (int k = i + 1; k < m; ++k) a = rl_fma(-w.CH[k + i * m], y[k], a);
+          y[i] = a * w.invh[i];
+        }
+        for (int i = 0; i < m; ++i) { if (c < n) w.L[i + c * m] = -y[i]; else w.dl[i] = -y[i]; }
+      }
+    });
+  }
+  phase(lane, [&](int l) {  // H L, H dl
+    for (int e = l; e < m * n + (HAS_DL ? m : 0); e += 32) {
+      if (e < m * n) {
+        int i = e % m, j = e / m;
+        double a = w.H[i] * w.L[j * m];
+        for (int k = 1; k < m; ++k) a = rl_fma(w.H[i + k * m], w.L[k + j * m], a);
+        w.HL[e] = a;
+      } else {
+        int i = e - m * n;
+        double a = w.H[i] * w.dl[0];
+        for (int k = 1; k < m; ++k) a = rl_fma(w.H[i + k * m], w.dl[k], a);
+        w.Hdl[i] = a;
+      }
+    }
+  });
+  double sval = w.q + s;
+  if (HAS_DL) {
+    double a = w.dl[0] * w.Hdl[0]; for (int k = 1; k < m; ++k) a = rl_fma(w.dl[k], w.Hdl[k], a);
+    double b = w.dl[0] * w.g[0]; for (int k = 1; k < m; ++k) b = rl_fma(w.dl[k], w.g[k], b);
+    sval = (sval + 0.5 * a) + b;
+  }
+  s = sval + extra;
+  phase(lane, [&](int l) {  // s_vec and S (upper), into the double buffers
+    for (int e = l; e < n + n * n; e += 32) {
+      if (e < n) {
+        int i = e;
+        double acc = w.qv[i] + coldot<Tr, KindA, n>(w.A, i, w.Dsv, 1);
+        if (HAS_DL) { double b = w.L[i * m] * w.Hdl[0]; for (int k = 1; k < m; ++k) b = rl_fma(w.L[k + i * m], w.Hdl[k], b); acc = acc + b; }
+        double c = w.L[i * m] * w.g[0]; for (int k = 1; k < m; ++k) c = rl_fma(w.L[k + i * m], w.g[k], c);
+        acc = acc + c;
+        if (HAS_DL) { double d = w.G[i * m] * w.dl[0]; for (int k = 1; k < m; ++k) d = rl_fma(w.G[k + i * m], w.dl[k], d); acc = acc + d; }
+        w.svn[i] = acc;
+      } else {
+        int f = e - n, i = f % n, j = f / n;
+        if (j < i) continue;
+        double a = coldot<Tr, KindA, n>(w.A, i, w.T + j * n, 1);
+        double acc = (Tr::q_kind(i, j) == 0) ? a : w.Q[i + j * n] + a;
+        double b = w.L[i * m] * w.HL[j * m]; for (int k = 1; k < m; ++k) b = rl_fma(w.L[k + i * m], w.HL[k + j * m], b);
+        acc = acc + b;
+        double c = w.L[i * m] * w.G[j * m]; for (int k = 1; k < m; ++k) c = rl_fma(w.L[k + i * m], w.G[k + j * m], c);
+        acc = acc + c;
+        double d = w.G[i * m] * w.L[j * m]; for (int k = 1; k < m; ++k) d = rl_fma(w.G[k + i * m], w.L[k + j * m], d);
+        acc = acc + d;
+        w.Sn[i + j * n] = acc;
+        w.Sn[j + i * n] = acc;
+      }
+    }
+  });
+  phase(lane, [&](int l) {
+    for (int e = l; e < n * n; e += 32) w.S[e] = w.Sn[e];
+    for (int e = l; e < n; e += 32) w.sv[e] = w.svn[e];
+  });
+  return 0;
+}
+
+// backward pass (approximate_model fused), cooperative; same contract as rl::backward_pass
+template <class D, class CT, bool OPT>
+RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, double theta, int buf, bool zeroL,
+                             double& mu, double& delta, int& restarts, double& value, CoopWs<D::n, D::m>& w,
+                             const CoopTraj& tj) {
+  constexpr int n = D::n, m = D::m;
+  using Tr = StageTraits<D, CT>;
+  const int N = P.N;
+  const double* Xb = tj.X + (size_t)buf * (N + 1) * n;
+  const double* Ub = tj.U + (size_t)buf * N * m;
+  while (true) {
+    double s = 0.0;
+    phase(lane, [&](int l) {
+      if (l != 0) return;
+      for (int i = 0; i < n; ++i) w.x[i] = Xb[(size_t)N * n + i];
+      double q;
+      w.flag = CT::terminal(cp, w.x, true, q, w.sv, w.Q) ? 0.0 : 1.0;  // :352-354
+      w.q = q;
+    });
+    if (w.flag != 0.0) return RATILQR_ST_DOMAIN;
+    s = w.q;
+    phase(lane, [&](int l) {
+      for (int e = l; e < n * n; e += 32) {
+        int i = e % n, j = e / n;
+        int a = i < j ? i : j, b2 = i < j ? j : i;  // Symmetric(): upper triangle mirrored
+        w.S[e] = (Tr::q_kind(a, b2) == 0) ? 0.0 : w.Q[a + b2 * n];
+      }
+    });
+    bool restart = false;
+    for (int k = N - 1; k >= 0; --k) {
+      double* Lk = tj.Lg + (size_t)k * m * n;
+      phase(lane, [&](int l) {
+        for (int e = l; e < n + m + m * n; e += 32) {
+          if (e < n) w.x[e] = Xb[(size_t)k * n + e];
+          else if (e < n + m) w.u[e - n] = Ub[(size_t)k * m + (e - n)];
+          else if (!OPT) w.L[e - n - m] = zeroL ? 0.0 : Lk[e - n - m];
+        }
+      });
+      phase(lane, [&](int l) {
+        if (l != 0) return;
+        double q;
+        w.flag = CT::stage(cp, k, w.x, w.u, true, q, w.qv, w.Q, w.r, w.R, w.Pm) ? 0.0 : 1.0;
+        w.q = q;
+      });
+      if (w.flag != 0.0) return RATILQR_ST_DOMAIN;
+      CoopJac<D>::run(lane, P.mp, w);
+      const size_t wo = P.W_tv ? (size_t)k * n * n : 0;
+      int rc = coop_riccati_stage<Tr, OPT, OPT>(lane, w, theta, mu, P.W + wo, P.Winv + wo, P.detW[P.W_tv ? k : 0], s);
+      if (rc == 1) return OPT ? RATILQR_ST_M_NOT_PD_OPT : RATILQR_ST_M_NOT_PD_INIT;
+      if (OPT) {
+        if (rc == 2) {
+          delta = fmax(P.delta_0, delta * P.delta_0);
+          mu = fmax(P.mu_min, mu * delta);
+          restarts++;
+          if (!(mu < 1e300)) return RATILQR_ST_MU_OVERFLOW;
+          restart = true;
+          break;
+        }
+        phase(lane, [&](int l) {
+          for (int e = l; e < m * n + m; e += 32) {
+            if (e < m * n) Lk[e] = w.L[e]; else tj.DL[(size_t)k * m + (e - m * n)] = w.dl[e - m * n];
+          }
+        });
+      }
+    }
+    if (!restart) { value = s; return 0; }
+  }
+}
+
+// closed-loop / open-loop (init) rollout into buffer cur^1, cooperative
+template <class D>
+RL_HD int coop_rollout(int lane, const SolveParams& P, int cur, double eps, bool init, double& dmax,
+                       CoopWs<D::n, D::m>& w, const CoopTraj& tj) {
+  constexpr int n = D::n, m = D::m;
+  const int N = P.N;
+  const double* Xc = tj.X + (size_t)cur * (N + 1) * n;
+  const double* Uc = tj.U + (size_t)cur * N * m;
+  double* Xn = tj.X + (size_t)(cur ^ 1) * (N + 1) * n;
+  double* Un = tj.U + (size_t)(cur ^ 1) * N * m;
+  phase(lane, [&](int l) { for (int i = l; i < n; i += 32) { w.x[i] = Xc[i]; Xn[i] = Xc[i]; } });
+  double best = -rl_inf();
+  bool has_nan = false;
+  for (int k = 0; k < N; ++k) {
+    const double* Lk = tj.Lg + (size_t)k * m * n;
+    phase(lane, [&](int l) {
+      for (int j = l; j < m; j += 32) {
+        const double lj = Uc[(size_t)k * m + j];
+        double uj = lj;
+        if (!init) {
+          double a = Lk[j] * (w.x[0] - Xc[(size_t)k * n]);
+          for (int i = 1; i < n; ++i) a = rl_fma(Lk[j + i * m], w.x[i] - Xc[(size_t)k * n + i], a);
+          uj = (lj + eps * tj.DL[(size_t)k * m + j]) + a;
+        }
+        w.u[j] = uj;
+        w.g[j] = lj - uj;  // scratch: l - u for the norm
+        Un[(size_t)k * m + j] = uj;
+      }
+    });
+    phase(lane, [&](int l) {
+      if (l != 0) return;
+      double acc = w.g[0] * w.g[0];
+      for (int j = 1; j < m; ++j) acc = rl_fma(w.g[j], w.g[j], acc);
+      w.nrm = sqrt(acc);
+      w.flag = D::f(P.mp, w.x, w.u, w.xn) ? 0.0 : 1.0;
+    });
+    const double nr = w.nrm;
+    if (nr != nr) has_nan = true;
+    if (nr > best) best = nr;
+    if (w.flag != 0.0) return RATILQR_ST_DOMAIN;
+    phase(lane, [&](int l) { for (int i = l; i < n; i += 32) { w.x[i] = w.xn[i]; Xn[(size_t)(k + 1) * n + i] = w.xn[i]; } });
+  }
+  dmax = has_nan ? (double)NAN : best;
+  return 0;
+}
+
+// the solve state machine of rl::solve_instance, executed by a whole warp for instance `inst`
+template <class D, class CT>
+RL_HD bool coop_solve_instance(int lane, const SolveParams& P, size_t inst, CoopWs<D::n, D::m>& w, const CoopTraj& tj, int& cur_out) {
+  constexpr int n = D::n, m = D::m;
+  const int N = P.N;
+  const size_t p = inst / (size_t)P.K;
+  if (P.active && !P.active[p]) return false;
+  const double* cp = P.cost_params + (P.cp_count > 1 ? p * (size_t)P.ncp : 0);
+  const double theta = P.theta[inst];
+  int cur = 1, iters = 0, trials = 0, restarts = 0, status = 0, count = 0;
+  double mu = 0.0, delta = P.delta_0, d_current = rl_inf(), value = rl_inf();
+  double eps_init = P.eps_init, eps = 0.0;
+  bool init = true, need_opt = false;
+  phase(lane, [&](int l) { for (int e = l; e < N * m * n; e += 32) tj.Lg[e] = 0.0; });  // initialize!: L = 0 (:230-232)
+  {
+    const double* x0 = P.x0 + (P.x0_count > 1 ? p * n : 0);
+    const double* ui = P.u_init + (P.u_count > 1 ? p * (size_t)m * N : 0);
+    double* Xc = tj.X + (size_t)cur * (N + 1) * n;
+    double* Uc = tj.U + (size_t)cur * N * m;
+    phase(lane, [&](int l) {
+      for (int i = l; i < n; i += 32) Xc[i] = x0[i];
+      for (int e = l; e < N * m; e += 32) Uc[e] = ui[e];
+    });
+  }
+  while (true) {
+    if (need_opt) {
+      double dummy;
+      status = coop_backward_pass<D, CT, true>(lane, P, cp, theta, cur, false, mu, delta, restarts, dummy, w, tj);
+      if (status) break;
+      need_opt = false;
+    }
+    if (!init) {
+      count++;
+      if (eps == 0.0 || count > 4000) { status = RATILQR_ST_LINESEARCH_HANG; break; }
+    }
+    double dmax, nw;
+    status = coop_rollout<D>(lane, P, cur, eps, init, dmax, w, tj);
+    if (status) break;
+    int rc = coop_backward_pass<D, CT, false>(lane, P, cp, theta, cur ^ 1, init, mu, delta, restarts, nw, w, tj);
+    if (rc == RATILQR_ST_DOMAIN) { status = rc; break; }
+    if (init) {
+      if (rc) { status = RATILQR_ST_M_NOT_PD_INIT; break; }
+      value = nw; cur ^= 1; init = false;
+      iters++; need_opt = true; eps = eps_init; count = 0;
+      continue;
+    }
+    if (rc) { eps *= P.lambda; continue; }
+    if (P.eps_hist && trials < P.eps_hist_cap && lane == 0) {
+      double* h = P.eps_hist + (inst * P.eps_hist_cap + trials) * 2;
+      h[0] = eps; h[1] = nw - value;
+    }
+    trials++;
+    bool accepted = isapprox_default(nw, value) || nw < value;
+    if (!accepted) {
+      eps *= P.lambda;
+      if (eps < P.eps_min) accepted = true;
+    }
+    if (!accepted) continue;
+    d_current = dmax; value = nw; cur ^= 1;
+    if (P.eps_auto) {
+      if (count == 1) eps_init = fmin(P.eps_init, eps / P.lambda);
+      else { while (eps < P.eps_min) eps = eps / P.lambda; eps_init = eps; }
+    }
+    if (P.d > d_current && mu <= P.mu_min) break;
+    if (iters == P.iter_max) break;
+    iters++; need_opt = true; eps = eps_init; count = 0;
+  }
+  if (status) value = rl_inf();
+  if (lane == 0) {
+    P.value[inst] = value;
+    P.status[inst] = status;
+    P.iters[inst] = iters;
+    P.trials[inst] = trials;
+    P.restarts[inst] = restarts;
+    P.mu_out[inst] = mu;
+    P.d_out[inst] = d_current;
+  }
+  cur_out = cur;
+  return true;
+}
+
+// final x_array, l_array, L_array in the host layout of the C ABI (instance slowest): plain contiguous copies
+template <int n, int m>
+RL_HD void coop_write_outputs(int lane, const SolveParams& P, size_t inst, const CoopTraj& tj, int cur) {
+  const int N = P.N;
+  phase(lane, [&](int l) {
+    if (P.xo) for (int e = l; e < (N + 1) * n; e += 32) P.xo[inst * (size_t)(N + 1) * n + e] = tj.X[(size_t)cur * (N + 1) * n + e];
+    if (P.lo) for (int e = l; e < N * m; e += 32) P.lo[inst * (size_t)N * m + e] = tj.U[(size_t)cur * N * m + e];
+    if (P.Lo) for (int e = l; e < N * m * n; e += 32) P.Lo[inst * (size_t)N * m * n + e] = tj.Lg[e];
+  });
+}
+
+}  // namespace rl

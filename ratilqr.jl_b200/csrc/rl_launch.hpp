@@ -11,6 +11,11 @@ namespace rll {
 // persistent one-thread-per-instance iLEQG solve (rl_kernels_solve.cu)
 int launch_solve(int model_id, int cost_id, const rl::SolveParams& P, cudaStream_t st);
 
+// warp-cooperative variant (rl_coop.cuh): one warp per instance; traj_global is the fallback trajectory storage
+// (B * coop_traj_doubles) used only when matrices + trajectories exceed the shared memory of an SM
+int coop_smem_query(int model_id, int cost_id, int N, size_t* smem_bytes);
+int launch_solve_coop(int model_id, int cost_id, const rl::SolveParams& P, double* traj_global, cudaStream_t st);
+
 // SoA workspace -> host-layout outputs (x, l, L), tile transpose through shared memory
 void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg, const int32_t* cur,
                    const int32_t* perm, double* x_out, double* l_out, double* L_out, cudaStream_t st);

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../ratilqr.jl_b200/csrc/rl_components.cuh"
+#include "../../ratilqr.jl_b200/csrc/rl_coop.cuh"
 #include "../../ratilqr.jl_b200/csrc/rl_host.hpp"
 
 using namespace rl;
@@ -39,7 +40,11 @@ static void ric(int N, int B, int optimise, const double* q, const double* qv, c
   }
 }
 
+static int g_coop = 0;  // 1: emulate the warp-cooperative kernel (32 virtual lanes run phase by phase)
+
 extern "C" {
+
+int32_t hostemu_set_coop(int32_t v) { g_coop = v; return 0; }
 
 int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
                                   const ratilqr_batch_in* in, ratilqr_ileqg_out* out) {
@@ -75,6 +80,36 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
   }
   P.perm = in->K >= 2 ? perm.data() : nullptr;
   const int cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
+  if (g_coop) {
+    std::vector<double> xo((size_t)n * (N + 1) * B), lo((size_t)m * N * B), Lo((size_t)m * n * N * B, 0.0);
+    P.perm = nullptr; P.xo = xo.data(); P.lo = lo.data(); P.Lo = Lo.data();
+    int rc2 = dispatch(desc->model_id, cost_id, [&](auto D, auto CT) {
+      using DD = decltype(D);
+      std::vector<double> traj(coop_traj_doubles(DD::n, DD::m, N));
+      for (size_t b = 0; b < B; ++b) {
+        CoopWs<DD::n, DD::m> w;
+        CoopTraj tj;
+        tj.X = traj.data(); tj.U = tj.X + (size_t)2 * (N + 1) * DD::n; tj.Lg = tj.U + (size_t)2 * N * DD::m; tj.DL = tj.Lg + (size_t)N * DD::m * DD::n;
+        int cur = 0;
+        if (coop_solve_instance<DD, decltype(CT)>(0, P, b, w, tj, cur)) coop_write_outputs<DD::n, DD::m>(0, P, b, tj, cur);
+      }
+    });
+    if (rc2) return rc2;
+    for (size_t b = 0; b < B; ++b) {
+      if (out->value) out->value[b] = value[b];
+      if (out->status) out->status[b] = status[b];
+      if (out->iters) out->iters[b] = iters[b];
+      if (out->trials) out->trials[b] = trials[b];
+      if (out->restarts) out->restarts[b] = restarts[b];
+      if (out->mu) out->mu[b] = mu[b];
+      if (out->d_current) out->d_current[b] = dcur[b];
+    }
+    if (out->x) memcpy(out->x, xo.data(), xo.size() * 8);
+    if (out->l) memcpy(out->l, lo.data(), lo.size() * 8);
+    if (out->L) memcpy(out->L, Lo.data(), Lo.size() * 8);
+    if (cap) memcpy(out->eps_hist, eps.data(), B * cap * 16);
+    return 0;
+  }
   int rc = dispatch(desc->model_id, cost_id, [&](auto D, auto CT) {
     double stage_area[2 * RL_STAGE_NV];
     Stage sg; sg.base = stage_area; sg.stride = 1;  // exercises the staged code path on the host

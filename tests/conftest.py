@@ -24,6 +24,14 @@ def hostemu_be():
     return _hostemu.load()
 
 
+@pytest.fixture
+def hostemu_coop_be(hostemu_be):
+    """the g++ build of the WARP-COOPERATIVE kernel arithmetic (32 virtual lanes run phase by phase)"""
+    hostemu_be.dll.hostemu_set_coop(1)
+    yield hostemu_be
+    hostemu_be.dll.hostemu_set_coop(0)
+
+
 @pytest.fixture(scope="session")
 def gpu_be():
     import ratilqr_b200 as R
@@ -32,7 +40,7 @@ def gpu_be():
     be.close()
 
 
-@pytest.fixture(params=["oracle", "hostemu", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.fixture(params=["oracle", "hostemu", "hostemu_coop", pytest.param("gpu", marks=pytest.mark.gpu)])
 def backend(request):
     """Every provider of the C ABI: the CPU oracle, the g++ build of the kernel arithmetic, the CUDA library."""
     return request.getfixturevalue(request.param + "_be")
