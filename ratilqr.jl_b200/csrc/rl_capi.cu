@@ -119,10 +119,11 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   UP(ctx->d_u, in->u_init, (size_t)m * N * in->u_count * 8);
   if (device_theta) CU(ctx->d_theta.reserve(B * 8));  // theta is produced on the device (fleet CE)
   else UP(ctx->d_theta, in->theta, B * 8);
-  CU(ctx->d_X.reserve(2 * (size_t)(N + 1) * n * B * 8));
-  CU(ctx->d_U.reserve(2 * (size_t)N * m * B * 8));
-  CU(ctx->d_Lg.reserve((size_t)N * m * n * B * 8));
-  CU(ctx->d_DL.reserve((size_t)N * m * B * 8));
+  const size_t Bp = (B + 31) / 32 * 32;  // the workspace is tiled in groups of 32 thread slots
+  CU(ctx->d_X.reserve(2 * (size_t)(N + 1) * n * Bp * 8));
+  CU(ctx->d_U.reserve(2 * (size_t)N * m * Bp * 8));
+  CU(ctx->d_Lg.reserve((size_t)N * m * n * Bp * 8));
+  CU(ctx->d_DL.reserve((size_t)N * m * Bp * 8));
   CU(ctx->d_value.reserve(B * 8));
   CU(ctx->d_mu.reserve(B * 8));
   CU(ctx->d_d.reserve(B * 8));
@@ -136,7 +137,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
     CU(cudaMemsetAsync(ctx->d_eps.p, 0, B * eps_cap * 16, ctx->stream));
   }
   // gains of instances that fail before their first optimising pass stay zero (initialize!: L = 0)
-  CU(cudaMemsetAsync(ctx->d_Lg.p, 0, (size_t)N * m * n * B * 8, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_Lg.p, 0, (size_t)N * m * n * Bp * 8, ctx->stream));
   rl::SolveParams& P = ctx->sp;
   memset(&P, 0, sizeof(P));
   P.N = N; P.B = (int)B; P.K = in->K;

@@ -35,9 +35,15 @@ RL_HD int comp_rollout_closed(const double* mp, const double* cp, int N, const d
     for (int i = 0; i < n; ++i) dx[i] = x[i] - xbar[(size_t)k * n + i];
     const double* Lk = L + (size_t)k * m * n;
     for (int j = 0; j < m; ++j) {
-      double a = Lk[j] * dx[0];
-      for (int i = 1; i < n; ++i) a = rl_fma(Lk[j + i * m], dx[i], a);
-      u[j] = l[(size_t)k * m + j] + a;
+      if (RL_FUSED) {  // same accumulation as rl::rollout_candidate
+        double uj = l[(size_t)k * m + j];
+        for (int i = 0; i < n; ++i) uj = rl_fma(Lk[j + i * m], dx[i], uj);
+        u[j] = uj;
+      } else {
+        double a = Lk[j] * dx[0];
+        for (int i = 1; i < n; ++i) a = rl_fma(Lk[j + i * m], dx[i], a);
+        u[j] = l[(size_t)k * m + j] + a;
+      }
       if (u_new) u_new[(size_t)k * m + j] = u[j];
     }
     if (cost) {

@@ -86,7 +86,7 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
     }
     extra = 0.5 * tr;
   } else {
-    phase(lane, [&](int l) { for (int e = l; e < n * n; e += 32) w.M[e] = Winv[e] - theta * w.S[e]; });
+    phase(lane, [&](int l) { for (int e = l; e < n * n; e += 32) w.M[e] = RL_FUSED ? rl_fma(-theta, w.S[e], Winv[e]) : Winv[e] - theta * w.S[e]; });
     // Cholesky in place, one column per step: lane i owns row i; the pivot is recomputed by every lane
     double detM = 1.0;
     int bad = 0;
@@ -144,16 +144,18 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
   });
   phase(lane, [&](int l) {  // g, G, H (upper mirrored)
     for (int e = l; e < m + m * n + m * m; e += 32) {
-      if (e < m) w.g[e] = w.r[e] + coldot<Tr, KindB, n>(w.B, e, w.Dsv, 1);
+      if (e < m) w.g[e] = RL_FUSED ? coldot_acc<Tr, KindB, n>(w.r[e], w.B, e, w.Dsv, 1) : w.r[e] + coldot<Tr, KindB, n>(w.B, e, w.Dsv, 1);
       else if (e < m + m * n) {
         int f = e - m, i = f % m, j = f / m;
+        if (RL_FUSED && Tr::p_kind(i, j) != 0) { w.G[f] = coldot_acc<Tr, KindB, n>(w.Pm[f], w.B, i, w.T + j * n, 1); continue; }
         double a = coldot<Tr, KindB, n>(w.B, i, w.T + j * n, 1);
         w.G[f] = (Tr::p_kind(i, j) == 0) ? a : w.Pm[f] + a;
       } else {
         int f = e - m - m * n, i = f % m, j = f / m;
         if (j < i) continue;
-        double a = coldot<Tr, KindB, n>(w.B, i, w.U + j * n, 1);
-        double h = (Tr::r_kind(i, j) == 0) ? a : w.R[i + j * m] + a;
+        double h;
+        if (RL_FUSED && Tr::r_kind(i, j) != 0) h = coldot_acc<Tr, KindB, n>(w.R[i + j * m], w.B, i, w.U + j * n, 1);
+        else { double a = coldot<Tr, KindB, n>(w.B, i, w.U + j * n, 1); h = (Tr::r_kind(i, j) == 0) ? a : w.R[i + j * m] + a; }
         if (i == j) h = h + mu;
         w.H[i + j * m] = h;
         w.H[j + i * m] = h;
@@ -212,14 +214,22 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
   double sval = w.q + s;
   if (HAS_DL) {
     double a = w.dl[0] * w.Hdl[0]; for (int k = 1; k < m; ++k) a = rl_fma(w.dl[k], w.Hdl[k], a);
-    double b = w.dl[0] * w.g[0]; for (int k = 1; k < m; ++k) b = rl_fma(w.dl[k], w.g[k], b);
-    sval = (sval + 0.5 * a) + b;
+    if (RL_FUSED) sval = dot_acc<m>(rl_fma(0.5, a, sval), w.dl, 1, w.g, 1);
+    else { double b = w.dl[0] * w.g[0]; for (int k = 1; k < m; ++k) b = rl_fma(w.dl[k], w.g[k], b); sval = (sval + 0.5 * a) + b; }
   }
   s = sval + extra;
   phase(lane, [&](int l) {  // s_vec and S (upper), into the double buffers
     for (int e = l; e < n + n * n; e += 32) {
       if (e < n) {
         int i = e;
+        if (RL_FUSED) {
+          double acc = coldot_acc<Tr, KindA, n>(w.qv[i], w.A, i, w.Dsv, 1);
+          if (HAS_DL) acc = dot_acc<m>(acc, w.L + i * m, 1, w.Hdl, 1);
+          acc = dot_acc<m>(acc, w.L + i * m, 1, w.g, 1);
+          if (HAS_DL) acc = dot_acc<m>(acc, w.G + i * m, 1, w.dl, 1);
+          w.svn[i] = acc;
+          continue;
+        }
         double acc = w.qv[i] + coldot<Tr, KindA, n>(w.A, i, w.Dsv, 1);
         if (HAS_DL) { double b = w.L[i * m] * w.Hdl[0]; for (int k = 1; k < m; ++k) b = rl_fma(w.L[k + i * m], w.Hdl[k], b); acc = acc + b; }
         double c = w.L[i * m] * w.g[0]; for (int k = 1; k < m; ++k) c = rl_fma(w.L[k + i * m], w.g[k], c);
@@ -229,6 +239,15 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
       } else {
         int f = e - n, i = f % n, j = f / n;
         if (j < i) continue;
+        if (RL_FUSED) {
+          double acc = (Tr::q_kind(i, j) == 0) ? coldot<Tr, KindA, n>(w.A, i, w.T + j * n, 1) : coldot_acc<Tr, KindA, n>(w.Q[i + j * n], w.A, i, w.T + j * n, 1);
+          acc = dot_acc<m>(acc, w.L + i * m, 1, w.HL + j * m, 1);
+          acc = dot_acc<m>(acc, w.L + i * m, 1, w.G + j * m, 1);
+          acc = dot_acc<m>(acc, w.G + i * m, 1, w.L + j * m, 1);
+          w.Sn[i + j * n] = acc;
+          w.Sn[j + i * n] = acc;
+          continue;
+        }
         double a = coldot<Tr, KindA, n>(w.A, i, w.T + j * n, 1);
         double acc = (Tr::q_kind(i, j) == 0) ? a : w.Q[i + j * n] + a;
         double b = w.L[i * m] * w.HL[j * m]; for (int k = 1; k < m; ++k) b = rl_fma(w.L[k + i * m], w.HL[k + j * m], b);
@@ -338,9 +357,14 @@ RL_HD int coop_rollout(int lane, const SolveParams& P, int cur, double eps, bool
         const double lj = Uc[(size_t)k * m + j];
         double uj = lj;
         if (!init) {
-          double a = Lk[j] * (w.x[0] - Xc[(size_t)k * n]);
-          for (int i = 1; i < n; ++i) a = rl_fma(Lk[j + i * m], w.x[i] - Xc[(size_t)k * n + i], a);
-          uj = (lj + eps * tj.DL[(size_t)k * m + j]) + a;
+          if (RL_FUSED) {
+            uj = lj + eps * tj.DL[(size_t)k * m + j];
+            for (int i = 0; i < n; ++i) uj = rl_fma(Lk[j + i * m], w.x[i] - Xc[(size_t)k * n + i], uj);
+          } else {
+            double a = Lk[j] * (w.x[0] - Xc[(size_t)k * n]);
+            for (int i = 1; i < n; ++i) a = rl_fma(Lk[j + i * m], w.x[i] - Xc[(size_t)k * n + i], a);
+            uj = (lj + eps * tj.DL[(size_t)k * m + j]) + a;
+          }
         }
         w.u[j] = uj;
         w.g[j] = lj - uj;  // scratch: l - u for the norm

@@ -53,8 +53,9 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
   const size_t B = (size_t)in->P * in->K;
   rlh::WPrep wp;
   if (!rlh::prep_W(n, N, desc->W, desc->W_time_varying, wp)) return -2;
-  std::vector<double> X(2 * (size_t)(N + 1) * n * B), U(2 * (size_t)N * m * B), Lg((size_t)N * m * n * B, 0.0),
-      DL((size_t)N * m * B), value(B), mu(B), dcur(B), eps;
+  const size_t Bp = (B + 31) / 32 * 32;  // warp-tiled workspace
+  std::vector<double> X(2 * (size_t)(N + 1) * n * Bp), U(2 * (size_t)N * m * Bp), Lg((size_t)N * m * n * Bp, 0.0),
+      DL((size_t)N * m * Bp), value(B), mu(B), dcur(B), eps;
   std::vector<int32_t> status(B), iters(B), trials(B), restarts(B), cur(B);
   int cap = out->eps_hist ? out->eps_hist_cap : 0;
   eps.assign(B * cap * 2 + 2, 0.0);
@@ -125,9 +126,10 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
     if (out->mu) out->mu[b] = mu[b];
     if (out->d_current) out->d_current[b] = dcur[b];
     size_t c = cur[b], inst = P.perm ? (size_t)P.perm[b] : b;  // b is the slot here
-    if (out->x) for (int e = 0; e < n * (N + 1); ++e) out->x[inst * n * (N + 1) + e] = X[(c * (N + 1) * n + e) * B + b];
-    if (out->l) for (int e = 0; e < m * N; ++e) out->l[inst * m * N + e] = U[(c * N * m + e) * B + b];
-    if (out->L) for (int e = 0; e < m * n * N; ++e) out->L[inst * m * n * N + e] = Lg[(size_t)e * B + b];
+    const size_t tb = b >> 5, ln = b & 31;
+    if (out->x) for (int e = 0; e < n * (N + 1); ++e) out->x[inst * n * (N + 1) + e] = X[((tb * 2 + c) * (N + 1) * n + e) * 32 + ln];
+    if (out->l) for (int e = 0; e < m * N; ++e) out->l[inst * m * N + e] = U[((tb * 2 + c) * N * m + e) * 32 + ln];
+    if (out->L) for (int e = 0; e < m * n * N; ++e) out->L[inst * m * n * N + e] = Lg[(tb * (size_t)N * m * n + e) * 32 + ln];
   }
   if (cap) memcpy(out->eps_hist, eps.data(), B * cap * 16);
   return 0;
