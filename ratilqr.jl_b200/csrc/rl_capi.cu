@@ -41,6 +41,9 @@ struct ratilqr_ctx {
   bool staged = false;
   int model_id = 0, cost_id = 0, n = 0, m = 0, N = 0, B = 0, eps_cap = 0;
   bool coop = false;          // staged solve runs on the warp-cooperative kernel
+  bool dynamic = false;       // staged solve uses the persistent kernel with lane-level refill
+  bool traj_retained = false; // xo/lo/Lo hold the trajectories (coop / dynamic modes)
+  DBuf d_queue;
   int coop_cost_id = 0;
   DBuf d_coop_traj;
   rl::SolveParams sp;
@@ -98,7 +101,7 @@ __global__ void k_ce_cost(int B, const double* value, const int32_t* status, con
 }
 
 static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
-                          const ratilqr_batch_in* in, int eps_cap, bool device_theta = false) {
+                          const ratilqr_batch_in* in, int eps_cap, bool device_theta = false, int want_traj = 0) {
   ctx->staged = false;
   if (const char* m = rlh::check_desc(desc, true)) FAIL(-1, m);
   if (const char* m = check_opts(opts)) FAIL(-3, m);
@@ -184,7 +187,25 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
     (void)capacity;
     ctx->coop = e ? (e[0] == '1') : (n > 6);
   }
+  ctx->dynamic = false;
+  ctx->traj_retained = false;
+  if (!ctx->coop) {
+    // Lane-level refill (persistent kernel pulling instances from a queue) is an opt-in experiment: measured
+    // SLOWER than the static theta-sorted assignment (148 vs 120 ms on the bench fleet, profiles/r01_dynamic_refill_ab.jsonl)
+    // because refilled lanes fall out of phase with their warp and most trips then carry a partially used optimising pass.
+    const char* e2 = getenv("RATILQR_DYNAMIC");
+    ctx->dynamic = (e2 && e2[0] == '1');
+    if (ctx->dynamic) {
+      CU(ctx->d_queue.reserve(8));
+      P.queue = ctx->d_queue.as<unsigned int>();
+      if (want_traj & 1) { CU(ctx->d_out1.reserve((size_t)n * (N + 1) * B * 8)); P.xo = ctx->d_out1.as<double>(); }
+      if (want_traj & 2) { CU(ctx->d_out2.reserve((size_t)m * N * B * 8)); P.lo = ctx->d_out2.as<double>(); }
+      if (want_traj & 4) { CU(ctx->d_out3.reserve((size_t)m * n * N * B * 8)); P.Lo = ctx->d_out3.as<double>(); }
+      ctx->traj_retained = true;
+    }
+  }
   if (ctx->coop) {
+    ctx->traj_retained = true;
     P.perm = nullptr;
     CU(ctx->d_out1.reserve((size_t)n * (N + 1) * B * 8));
     CU(ctx->d_out2.reserve((size_t)m * N * B * 8));
@@ -209,6 +230,7 @@ static int run_internal(ratilqr_ctx* ctx, int reps, float* ms_total) {
       if (int rc = check_launch(ctx, "k_ileqg_solve_coop")) return rc;
       continue;
     }
+    if (ctx->dynamic) CU(cudaMemsetAsync(ctx->sp.queue, 0, 4, ctx->stream));
     if (rll::launch_solve(ctx->model_id, ctx->cost_id, ctx->sp, ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
     if (int rc = check_launch(ctx, "k_ileqg_solve")) return rc;
   }
@@ -228,10 +250,14 @@ static int fetch_internal(ratilqr_ctx* ctx, ratilqr_ileqg_out* out) {
   const size_t B = (size_t)ctx->B;
   cudaStream_t st = ctx->stream;
   double *dx = nullptr, *dl = nullptr, *dL = nullptr;
-  if (out->x) { CU(ctx->d_out1.reserve((size_t)n * (N + 1) * B * 8)); dx = ctx->d_out1.as<double>(); }
-  if (out->l) { CU(ctx->d_out2.reserve((size_t)m * N * B * 8)); dl = ctx->d_out2.as<double>(); }
-  if (out->L) { CU(ctx->d_out3.reserve((size_t)m * n * N * B * 8)); dL = ctx->d_out3.as<double>(); }
-  if (ctx->coop) {  // the cooperative kernel already wrote x, l, L in host layout
+  if (!ctx->traj_retained) {
+    if (out->x) { CU(ctx->d_out1.reserve((size_t)n * (N + 1) * B * 8)); dx = ctx->d_out1.as<double>(); }
+    if (out->l) { CU(ctx->d_out2.reserve((size_t)m * N * B * 8)); dl = ctx->d_out2.as<double>(); }
+    if (out->L) { CU(ctx->d_out3.reserve((size_t)m * n * N * B * 8)); dL = ctx->d_out3.as<double>(); }
+  }
+  if (ctx->traj_retained) {  // the cooperative / persistent kernels wrote x, l, L in host layout themselves
+    if ((out->x && !ctx->sp.xo) || (out->l && !ctx->sp.lo) || (out->L && !ctx->sp.Lo))
+      FAIL(-4, "trajectories were not retained by this staged solve: request them through ratilqr_ileqg_solve_batch");
     dx = out->x ? ctx->sp.xo : nullptr; dl = out->l ? ctx->sp.lo : nullptr; dL = out->L ? ctx->sp.Lo : nullptr;
   } else if (dx || dl || dL) {
     rll::launch_gather(n, m, N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.cur, ctx->sp.perm, dx, dl, dL, st);
@@ -297,7 +323,7 @@ int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
   DBuf* all[] = {&ctx->d_cp, &ctx->d_W, &ctx->d_Winv, &ctx->d_detW, &ctx->d_x0, &ctx->d_u, &ctx->d_theta, &ctx->d_X,
                  &ctx->d_U, &ctx->d_Lg, &ctx->d_DL, &ctx->d_value, &ctx->d_status, &ctx->d_iters, &ctx->d_trials,
                  &ctx->d_restarts, &ctx->d_mu, &ctx->d_d, &ctx->d_cur, &ctx->d_eps, &ctx->d_perm, &ctx->d_out1, &ctx->d_out2,
-                 &ctx->d_out3, &ctx->d_cost, &ctx->d_coop_traj};
+                 &ctx->d_out3, &ctx->d_cost, &ctx->d_coop_traj, &ctx->d_queue};
   for (DBuf* b : all) b->release();
   for (DBuf& b : ctx->s) b.release();
   cudaEventDestroy(ctx->ev0);
@@ -336,7 +362,8 @@ int32_t ratilqr_ileqg_solve_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* 
                                   const ratilqr_batch_in* in, ratilqr_ileqg_out* out) {
   if (!ctx) return -1;
   if (!out) FAIL(-1, "null out");
-  int rc = stage_internal(ctx, desc, opts, in, out->eps_hist ? out->eps_hist_cap : 0);
+  const int want = (out->x ? 1 : 0) | (out->l ? 2 : 0) | (out->L ? 4 : 0);
+  int rc = stage_internal(ctx, desc, opts, in, out->eps_hist ? out->eps_hist_cap : 0, false, want);
   if (rc) return rc;
   rc = run_internal(ctx, 1, nullptr);
   if (rc) return rc;
@@ -708,7 +735,8 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   }
   // final solve at theta_opt with the retry rule (:390-414); B = P instances, theta on the device
   in.K = 1;
-  if ((rc = stage_internal(ctx, desc, opts, &in, final_out && final_out->eps_hist ? final_out->eps_hist_cap : 0, true))) return rc;
+  const int fwant = final_out ? ((final_out->x ? 1 : 0) | (final_out->l ? 2 : 0) | (final_out->L ? 4 : 0)) : 0;
+  if ((rc = stage_internal(ctx, desc, opts, &in, final_out && final_out->eps_hist ? final_out->eps_hist_cap : 0, true, fwant))) return rc;
   rll::launch_ce_pick_theta(c, ctx->d_theta.as<double>(), st);
   if ((rc = check_launch(ctx, "k_ce_pick_theta"))) return rc;
   ctx->sp.active = c.active;

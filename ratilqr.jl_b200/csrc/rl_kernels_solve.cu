@@ -25,14 +25,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_ileqg_solve(const __grid_cons
   Stage sg;
   sg.base = (UseStage<D>::value && P.use_stage) ? stage_area + threadIdx.x : nullptr;
   sg.stride = THREADS;
-  if (b < (size_t)P.B) solve_instance<D, CT>(P, b, sg);
+  if (P.queue) solve_dynamic<D, CT>(P, b, sg);  // persistent: every thread keeps pulling instances
+  else if (b < (size_t)P.B) solve_instance<D, CT>(P, b, sg);
 }
 
 template <class D, class CT, int THREADS, int MINB>
 static void launch_shape(const SolveParams& P, cudaStream_t st) {
-  const int blocks = (P.B + THREADS - 1) / THREADS;
+  int blocks = (P.B + THREADS - 1) / THREADS;
   const size_t smem = UseStage<D>::value ? (size_t)2 * RL_STAGE_NV * THREADS * sizeof(double) : 0;
   static bool configured = false;
+  static int resident = MINB, sms = 148;
   if (!configured) {
     configured = true;
     auto kfn = k_ileqg_solve<D, CT, THREADS, MINB>;
@@ -42,12 +44,16 @@ static void launch_shape(const SolveParams& P, cudaStream_t st) {
       int pct = (int)((MINB * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 5;
       cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
     }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, THREADS, smem);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (getenv("RATILQR_DEBUG")) {
-      int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, THREADS, smem);
+      int nb = resident;
       fprintf(stderr, "[ratilqr] k_ileqg_solve threads=%d minb=%d smem=%zu -> %d resident CTAs/SM\n", THREADS, MINB, smem, nb);
     }
   }
+  if (P.queue && blocks > resident * sms) blocks = resident * sms;  // persistent grid: exactly one resident wave
   k_ileqg_solve<D, CT, THREADS, MINB><<<blocks, THREADS, smem, st>>>(P);
 }
 

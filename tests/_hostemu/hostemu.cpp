@@ -40,11 +40,13 @@ static void ric(int N, int B, int optimise, const double* q, const double* qv, c
   }
 }
 
+static int g_dynamic = 0;  // 1: emulate the opt-in persistent kernel with lane-level refill (RATILQR_DYNAMIC=1)
 static int g_coop = 0;  // 1: emulate the warp-cooperative kernel (32 virtual lanes run phase by phase)
 
 extern "C" {
 
 int32_t hostemu_set_coop(int32_t v) { g_coop = v; return 0; }
+int32_t hostemu_set_dynamic(int32_t v) { g_dynamic = v; return 0; }
 
 int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
                                   const ratilqr_batch_in* in, ratilqr_ileqg_out* out) {
@@ -111,11 +113,36 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
     if (cap) memcpy(out->eps_hist, eps.data(), B * cap * 16);
     return 0;
   }
+  // g_dynamic: emulate the persistent kernel (lane-level refill).  Threads run one after another here, so slot 0
+  // drains most of the queue: a maximal test of workspace-slot reuse across instances.
+  unsigned int queue = 0;
+  std::vector<double> xo, lo, Lo;
+  if (g_dynamic) {
+    xo.assign((size_t)n * (N + 1) * B, 0.0); lo.assign((size_t)m * N * B, 0.0); Lo.assign((size_t)m * n * N * B, 0.0);
+    P.queue = &queue; P.xo = xo.data(); P.lo = lo.data(); P.Lo = Lo.data();
+  }
   int rc = dispatch(desc->model_id, cost_id, [&](auto D, auto CT) {
     double stage_area[2 * RL_STAGE_NV];
     Stage sg; sg.base = stage_area; sg.stride = 1;  // exercises the staged code path on the host
-    for (size_t b = 0; b < B; ++b) solve_instance<decltype(D), decltype(CT)>(P, b, sg);
+    if (g_dynamic) { for (size_t b = 0; b < std::min<size_t>(B, 3); ++b) solve_dynamic<decltype(D), decltype(CT)>(P, b, sg); }
+    else { for (size_t b = 0; b < B; ++b) solve_instance<decltype(D), decltype(CT)>(P, b, sg); }
   });
+  if (!rc && g_dynamic) {
+    for (size_t b = 0; b < B; ++b) {
+      if (out->value) out->value[b] = value[b];
+      if (out->status) out->status[b] = status[b];
+      if (out->iters) out->iters[b] = iters[b];
+      if (out->trials) out->trials[b] = trials[b];
+      if (out->restarts) out->restarts[b] = restarts[b];
+      if (out->mu) out->mu[b] = mu[b];
+      if (out->d_current) out->d_current[b] = dcur[b];
+    }
+    if (out->x) memcpy(out->x, xo.data(), xo.size() * 8);
+    if (out->l) memcpy(out->l, lo.data(), lo.size() * 8);
+    if (out->L) memcpy(out->L, Lo.data(), Lo.size() * 8);
+    if (cap) memcpy(out->eps_hist, eps.data(), B * cap * 16);
+    return 0;
+  }
   if (rc) return rc;
   for (size_t b = 0; b < B; ++b) {
     if (out->value) out->value[b] = value[b];

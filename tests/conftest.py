@@ -32,6 +32,14 @@ def hostemu_coop_be(hostemu_be):
     hostemu_be.dll.hostemu_set_coop(0)
 
 
+@pytest.fixture
+def hostemu_dynamic_be(hostemu_be):
+    """the opt-in persistent variant (lane-level refill from an instance queue): heavy workspace-slot reuse"""
+    hostemu_be.dll.hostemu_set_dynamic(1)
+    yield hostemu_be
+    hostemu_be.dll.hostemu_set_dynamic(0)
+
+
 @pytest.fixture(scope="session")
 def gpu_be():
     import ratilqr_b200 as R

@@ -21,7 +21,7 @@ def relerr(a, b):
     return float(np.max(np.abs(a[fin] - b[fin])) / max(np.max(np.abs(b[fin])), 1e-300))
 
 
-@pytest.fixture(params=["hostemu", "hostemu_coop", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.fixture(params=["hostemu", "hostemu_dynamic", "hostemu_coop", pytest.param("gpu", marks=pytest.mark.gpu)])
 def dut(request):
     return request.getfixturevalue(request.param + "_be")
 
