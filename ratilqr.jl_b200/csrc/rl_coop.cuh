@@ -70,7 +70,7 @@ template <> struct CoopJac<Dyn<RATILQR_MODEL_QUADROTOR>> {
 // returns 0 / 1 (M not PD) / 2 (H not PD); identical arithmetic per output element to rl::riccati_stage.
 template <class Tr, bool OPT, bool HAS_DL>
 RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, double mu, const double* RL_RESTRICT W,
-                             const double* RL_RESTRICT Winv, double detW, double& s) {
+                             const double* RL_RESTRICT Winv, double detW, double& s, double* detprod = nullptr) {
   constexpr int n = Tr::n, m = Tr::m;
   double extra = 0.0;
   if (theta == 0.0) {
@@ -134,7 +134,8 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
     });
     double quad = w.z[0] * w.z[0];
     for (int k = 1; k < n; ++k) quad = rl_fma(w.z[k], w.z[k], quad);
-    extra = (theta / 2) * quad - (1 / (2 * theta)) * log(detW * detM);
+    if (detprod) { *detprod *= detW * detM; extra = (theta / 2) * quad; }
+    else extra = (theta / 2) * quad - (1 / (2 * theta)) * log(detW * detM);
   }
   phase(lane, [&](int l) {  // T = (D S+) A, U = (D S+) B
     for (int e = l; e < n * n + n * m; e += 32) {
@@ -224,8 +225,8 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
         int i = e;
         if (RL_FUSED) {
           double acc = coldot_acc<Tr, KindA, n>(w.qv[i], w.A, i, w.Dsv, 1);
-          if (HAS_DL) acc = dot_acc<m>(acc, w.L + i * m, 1, w.Hdl, 1);
-          acc = dot_acc<m>(acc, w.L + i * m, 1, w.g, 1);
+          if (HAS_DL) { double t[m]; for (int k = 0; k < m; ++k) t[k] = w.Hdl[k] + w.g[k]; acc = dot_acc<m>(acc, w.L + i * m, 1, t, 1); }
+          else acc = dot_acc<m>(acc, w.L + i * m, 1, w.g, 1);
           if (HAS_DL) acc = dot_acc<m>(acc, w.G + i * m, 1, w.dl, 1);
           w.svn[i] = acc;
           continue;
@@ -241,8 +242,7 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
         if (j < i) continue;
         if (RL_FUSED) {
           double acc = (Tr::q_kind(i, j) == 0) ? coldot<Tr, KindA, n>(w.A, i, w.T + j * n, 1) : coldot_acc<Tr, KindA, n>(w.Q[i + j * n], w.A, i, w.T + j * n, 1);
-          acc = dot_acc<m>(acc, w.L + i * m, 1, w.HL + j * m, 1);
-          acc = dot_acc<m>(acc, w.L + i * m, 1, w.G + j * m, 1);
+          { double t[m]; for (int k = 0; k < m; ++k) t[k] = w.HL[k + j * m] + w.G[k + j * m]; acc = dot_acc<m>(acc, w.L + i * m, 1, t, 1); }
           acc = dot_acc<m>(acc, w.G + i * m, 1, w.L + j * m, 1);
           w.Sn[i + j * n] = acc;
           w.Sn[j + i * n] = acc;
@@ -297,6 +297,7 @@ RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, d
       }
     });
     bool restart = false;
+    double detprod = 1.0, logacc = 0.0;
     for (int k = N - 1; k >= 0; --k) {
       double* Lk = tj.Lg + (size_t)k * m * n;
       phase(lane, [&](int l) {
@@ -315,8 +316,9 @@ RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, d
       if (w.flag != 0.0) return RATILQR_ST_DOMAIN;
       CoopJac<D>::run(lane, P.mp, w);
       const size_t wo = P.W_tv ? (size_t)k * n * n : 0;
-      int rc = coop_riccati_stage<Tr, OPT, OPT>(lane, w, theta, mu, P.W + wo, P.Winv + wo, P.detW[P.W_tv ? k : 0], s);
+      int rc = coop_riccati_stage<Tr, OPT, OPT>(lane, w, theta, mu, P.W + wo, P.Winv + wo, P.detW[P.W_tv ? k : 0], s, RL_FUSED ? &detprod : nullptr);
       if (rc == 1) return OPT ? RATILQR_ST_M_NOT_PD_OPT : RATILQR_ST_M_NOT_PD_INIT;
+      if (RL_FUSED && !(detprod > 1e-250 && detprod < 1e250)) { logacc += log(detprod); detprod = 1.0; }
       if (OPT) {
         if (rc == 2) {
           delta = fmax(P.delta_0, delta * P.delta_0);
@@ -333,7 +335,11 @@ RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, d
         });
       }
     }
-    if (!restart) { value = s; return 0; }
+    if (!restart) {
+      if (RL_FUSED && theta != 0.0) s = s - (1 / (2 * theta)) * (logacc + log(detprod));
+      value = s;
+      return 0;
+    }
   }
 }
 

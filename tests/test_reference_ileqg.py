@@ -147,10 +147,14 @@ def test_whole_solve_equals_host_stepping(backend):
             if b.iter_current == b.iter_max:
                 break
         assert b.iter_current == a.iter_current
-        assert va == b.value_current
+        # trajectories and gains never depend on the scalar s, so they agree bit for bit; the value itself differs in
+        # the last ulps because the persistent kernel takes ONE log per pass (log of the product of the stage
+        # determinants) while the component pass, like the reference, takes one per stage
+        assert np.isclose(va, b.value_current, rtol=1e-13)
         assert all(np.array_equal(p, q) for p, q in zip(xa, b.x_array))
         assert all(np.array_equal(p, q) for p, q in zip(La, b.L_array))
-        assert ha == b.eps_history
+        assert len(ha) == len(b.eps_history)
+        assert all(e1 == e2 and abs(d1 - d2) <= 1e-13 * max(1.0, abs(va)) for (e1, d1), (e2, d2) in zip(ha, b.eps_history))
 
 
 def test_neurotic_breakdown_and_domain_error(backend):
