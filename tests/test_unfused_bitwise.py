@@ -1,0 +1,38 @@
+"""The kernel arithmetic compiled with -DRL_FUSED=0 (no fused accumulation, IEEE 1/sqrt, one log per stage) follows
+the oracle's canonical order exactly: results must be BIT-IDENTICAL, for the thread-per-instance formulation and for
+the warp-cooperative one.  (The shipped kernels use RL_FUSED=1 and are compared at 1e-9 elsewhere.)"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ratilqr_b200 import workloads as wl
+from ratilqr_b200._capi import CApi
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_hostemu")
+
+
+@pytest.fixture(scope="module")
+def unfused():
+    subprocess.check_call(["make", "-C", HERE, "-s", "libhostemu_unfused.so"])
+    return CApi(ctypes.CDLL(os.path.join(HERE, "libhostemu_unfused.so")), "hostemu_", needs_ctx=False)
+
+
+@pytest.mark.parametrize("coop", [0, 1])
+def test_unfused_build_is_bit_identical_to_oracle(unfused, oracle_be, coop):
+    unfused.dll.hostemu_set_coop(coop)
+    try:
+        for prob, x0, u, th in ((*wl.c1_problem(), [0.0, 0.1, 0.43, 30.7, 40.0]), (*wl.c2_problem(), wl.c2_thetas(96)),
+                                (*wl.c3_problem(N=8), [0.0, 0.05])):
+            spec = prob.spec()
+            a = oracle_be.ileqg_solve_batch(spec, x0, u, th, eps_hist_cap=64)
+            b = unfused.ileqg_solve_batch(spec, x0, u, th, eps_hist_cap=64)
+            for k in ("status", "iters", "trials", "restarts"):
+                assert np.array_equal(a[k], b[k]), k
+            ok = a["status"] == 0
+            for k in ("value", "x", "l", "L", "eps_hist"):
+                assert np.array_equal(a[k][..., ok], b[k][..., ok]), k
+    finally:
+        unfused.dll.hostemu_set_coop(0)
