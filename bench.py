@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems", type=int, default=444, help="independent unicycle problems per GPU (x 1024 theta each)")
+    ap.add_argument("--fleet-problems", type=int, default=8192, help="RAT iLQR problems per GPU for the MPC-step figure")
     ap.add_argument("--cpu-sample-problems", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -226,6 +227,20 @@ def main():
     h2d = int(x0.nbytes + u.nbytes + theta.nbytes + spec.cost_params.nbytes + spec.W.nbytes * 3)
     d2h = int(cost.nbytes + st.nbytes)
 
+    # ---- second half of the metric: RAT iLQR MPC step latency (configs[4]: fleet of independent unicycle problems,
+    #      CE defaults 10 theta x 5 iterations + final solve, whole loop on the device, host buffers in/out) ----------
+    Pf = args.fleet_problems
+    from ratilqr_b200 import workloads as wl
+    fprob, fcps, fx0, fu = wl.fleet(Pf, key=70 + rank)
+    fspec = fprob.spec(cost_params=fcps)
+    be.ce_solve_fleet(fspec, fx0, fu, 0.1, 1.0, 2.0, seed=7 + rank, want=())  # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    fr = be.ce_solve_fleet(fspec, fx0, fu, 0.1, 1.0, 2.0, seed=7 + rank, want=("l",))
+    barrier()
+    fleet_s = max_over_ranks(time.perf_counter() - t0)
+    fleet_ok = sum_over_ranks(float((fr["status"] == 0).sum()))
+
     out = None
     if rank == 0:
         peak_tf = be.fp64_probe()
@@ -264,7 +279,12 @@ def main():
                "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
                "c2_single": {"workload": "configs[1] exactly: 1 problem x 1024 theta", "ms_per_batch": ms1,
-                             "solves_per_sec": THETAS / (ms1 * 1e-3)}}
+                             "solves_per_sec": THETAS / (ms1 * 1e-3)},
+               "mpc_step": {"workload": f"configs[4]: fleet of {Pf} independent RAT iLQR unicycle problems per GPU (CE: 10 theta x 5 "
+                                        "iterations + final solve), ratilqr_ce_solve_fleet, host buffers in, theta_opt/value/l out",
+                            "ms_per_fleet_step": fleet_s * 1e3, "problems_per_sec": Pf * world / fleet_s,
+                            "us_per_problem_step": fleet_s * 1e6 / (Pf * world), "ce_rounds": fr["rounds"],
+                            "final_solves_ok": int(fleet_ok), "problems": Pf * world}}
         if not args.no_cpu_baseline:
             v, cores, dt = cpu_arm(lambda PP: build_inputs(PP, 0), args.cpu_sample_problems, 1, 0)
             out["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",

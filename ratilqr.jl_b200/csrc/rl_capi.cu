@@ -242,6 +242,28 @@ static int run_internal(ratilqr_ctx* ctx, int reps, float* ms_total) {
   return 0;
 }
 
+// Fleet scheduling: order the thread slots by the work each PROBLEM needed in the previous launch (max iterations
+// over its instances), so that the 32 lanes of a warp hold problems of similar length.  Host-side argsort of P keys
+// (the fleet loop synchronises once per round anyway).
+#include <algorithm>
+#include <numeric>
+static int resort_slots_by_last_iters(ratilqr_ctx* ctx, int P, int K) {
+  const size_t B = (size_t)P * K;
+  std::vector<int32_t> iters(B), perm(B);
+  CU(cudaMemcpyAsync(iters.data(), ctx->sp.iters, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t> key(P), order(P);
+  for (int p = 0; p < P; ++p) { int32_t mx = 0; for (int j = 0; j < K; ++j) mx = std::max(mx, iters[(size_t)p * K + j]); key[p] = mx; }
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  for (int r = 0; r < P; ++r) for (int j = 0; j < K; ++j) perm[(size_t)r * K + j] = (int32_t)((size_t)order[r] * K + j);
+  CU(ctx->d_perm.reserve(B * 4));
+  CU(cudaMemcpyAsync(ctx->d_perm.p, perm.data(), B * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // perm is a stack vector
+  ctx->sp.perm = ctx->d_perm.as<int32_t>();
+  return 0;
+}
+
 static int fetch_internal(ratilqr_ctx* ctx, ratilqr_ileqg_out* out) {
   if (!ctx->staged) FAIL(-4, "nothing staged");
   if (!out) FAIL(-1, "null out");
@@ -686,6 +708,8 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   ratilqr_batch_in in;
   in.P = P; in.K = S; in.x0 = x0; in.x0_count = x0_count; in.u_init = u_init; in.u_count = u_count; in.theta = nullptr;
   int rc = 0, rounds = 0;
+  const char* esf = getenv("RATILQR_FLEET_SORT");  // 0 disables the iteration-count ordering of slots (A/B runs)
+  const bool sort_fleet = !(esf && esf[0] == '0');
   const size_t Pb = (size_t)P * 8;
   std::vector<double> init_tmin(P, HUGE_VAL), zeros(P, 0.0);
   std::vector<int32_t> ones(P, 1), izeros(P, 0);
@@ -731,7 +755,16 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
       rounds++;
       if (n_active == 0) break;
       if (rounds > 100000) FAIL(-6, "CE redraw loop does not terminate (the reference would spin forever here)");
+      if (sort_fleet && !ctx->coop && P >= 64) { if ((rc = resort_slots_by_last_iters(ctx, P, S))) return rc; }
     }
+  }
+  std::vector<int32_t> last_key;
+  if (kl_bound > 0 && sort_fleet && !ctx->coop && P >= 64) {  // per-problem work of the last round orders the final solve too
+    std::vector<int32_t> it((size_t)P * S);
+    CU(cudaMemcpyAsync(it.data(), ctx->sp.iters, it.size() * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    last_key.resize(P);
+    for (int p = 0; p < P; ++p) { int32_t mx = 0; for (int j = 0; j < S; ++j) mx = std::max(mx, it[(size_t)p * S + j]); last_key[p] = mx; }
   }
   // final solve at theta_opt with the retry rule (:390-414); B = P instances, theta on the device
   in.K = 1;
@@ -740,6 +773,15 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   rll::launch_ce_pick_theta(c, ctx->d_theta.as<double>(), st);
   if ((rc = check_launch(ctx, "k_ce_pick_theta"))) return rc;
   ctx->sp.active = c.active;
+  if (!last_key.empty() && !ctx->coop) {
+    std::vector<int32_t> order(P);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return last_key[a] < last_key[b]; });
+    CU(ctx->d_perm.reserve((size_t)P * 4));
+    CU(cudaMemcpyAsync(ctx->d_perm.p, order.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->sp.perm = ctx->d_perm.as<int32_t>();
+  }
   int final_rounds = 0;
   while (true) {
     if ((rc = run_internal(ctx, 1, nullptr))) return rc;
