@@ -161,6 +161,22 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
                                double* mu, double* sigma, int64_t* nz_used, int32_t* rounds,
                                ratilqr_ileqg_out* final);
 
+/* solve!(::NelderMeadBilevelOptimizationSolver, ...) (nelder_mead_bilevel_optimization.jl:276-352) for a fleet of P
+ * independent problems in lock-step rounds.  Evaluations are pure functions of theta, so every round solves, in ONE
+ * batched launch, all candidates the decision tree of step! (:174-252) can ask for (theta_r, theta_e, both possible
+ * contractions, both shrink points) and then replays the tree per problem on the device: visited vertices and
+ * returned values equal the serial order.  theta_high_init / theta_low_init (P, in-out) and the vertex costs
+ * c_high / c_low with their has_c flags (P, in-out) persist across calls like the fields of the Julia struct. */
+typedef struct {
+  double alpha, beta, gamma, eps, lambda; int32_t iter_max;
+} ratilqr_nm_opts;
+int32_t ratilqr_nm_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                               const ratilqr_nm_opts* nm, int32_t P, const double* x0, int32_t x0_count,
+                               const double* u_init, int32_t u_count, double kl_bound,
+                               double* theta_high_init, double* theta_low_init, double* c_high, double* c_low,
+                               int32_t* has_c, double* theta_opt, double* value, int32_t* nm_iters, int32_t* n_evals,
+                               ratilqr_ileqg_out* final);
+
 /* Device-resident variant used for throughput measurement: stage once, run many times.
  * stage = H2D of inputs; run = the solve kernel only, `reps` launches back to back on the
  * ctx stream, bracketed by CUDA events recorded on that stream (ms_total out);

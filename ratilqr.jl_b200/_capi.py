@@ -65,6 +65,11 @@ class CeOpts(C.Structure):  # ratilqr_ce_opts
                 ("use_theta_max", C.c_int32)]
 
 
+class NmOpts(C.Structure):  # ratilqr_nm_opts
+    _fields_ = [("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double), ("eps", C.c_double), ("lam", C.c_double),
+                ("iter_max", C.c_int32)]
+
+
 def _dp(a):
     return None if a is None else a.ctypes.data_as(c_double_p)
 
@@ -164,6 +169,8 @@ class CApi:
         self.f_ce_fleet = self._fn("ce_solve_fleet", [vp, PD, IO, C.POINTER(CeOpts), i32, dp, i32, dp, i32, f64, dp, C.c_int64,
                                                       C.c_uint64, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int64),
                                                       ip, OUT])
+        self.f_nm_fleet = self._fn("nm_solve_fleet", [vp, PD, IO, C.POINTER(NmOpts), i32, dp, i32, dp, i32, f64, dp, dp, dp, dp, ip,
+                                                      dp, dp, ip, ip, OUT])
         self.f_stage = self._fn("ileqg_stage", [vp, PD, IO, BI])
         self.f_run = self._fn("ileqg_run", [vp, i32, C.POINTER(C.c_float)])
         self.f_fetch = self._fn("ileqg_fetch", [vp, OUT])
@@ -269,6 +276,40 @@ class CApi:
                                     _dp(res["sigma"]), res["nz_used"].ctypes.data_as(C.POINTER(C.c_int64)), C.byref(rounds),
                                     C.byref(out)), "ce_solve_fleet")
         res["mu_init"], res["sigma_init"], res["rounds"] = mu_i, sg_i, int(rounds.value)
+        return res
+
+    def nm_solve_fleet(self, spec, x0, u_init, kl_bound, state=None, alpha=1.0, beta=2.0, gamma=0.5, eps=1e-2, lam=0.5,
+                       iter_max=100, theta_high_init=3.0, theta_low_init=1e-8, opts=None, want=("x", "l", "L")):
+        """solve!(::NelderMeadBilevelOptimizationSolver) for P problems at once (nelder_mead...:276-352).
+        `state` (returned by a previous call) carries theta_*_init, c_high, c_low, has_c across calls like the Julia struct."""
+        opts = opts or make_opts()
+        n, m, N = spec.n, spec.m, spec.N
+        x0 = np.asarray(x0, dtype=np.float64).reshape(n, -1)
+        P = max(x0.shape[1], spec.cost_params_count)
+        u_init = np.asarray(u_init, dtype=np.float64)
+        u_count = 1 if u_init.ndim == 2 else u_init.shape[-1]
+        x0f, uf = _f64(x0), _f64(u_init)
+        if state is None:
+            state = dict(theta_high_init=np.full(P, float(theta_high_init)), theta_low_init=np.full(P, float(theta_low_init)),
+                         c_high=np.zeros(P), c_low=np.zeros(P), has_c=np.zeros((P, 2), np.int32))
+        st = {k: np.ascontiguousarray(v).copy() for k, v in state.items()}
+        res = dict(theta_opt=np.zeros(P), value=np.zeros(P), nm_iters=np.zeros(P, np.int32), n_evals=np.zeros(P, np.int32),
+                   status=np.zeros(P, np.int32))
+        if "x" in want:
+            res["x"] = np.zeros((n, N + 1, P), order="F")
+        if "l" in want:
+            res["l"] = np.zeros((m, N, P), order="F")
+        if "L" in want:
+            res["L"] = np.zeros((m, n, N, P), order="F")
+        out = IleqgOut(_dp(res.get("x")), _dp(res.get("l")), _dp(res.get("L")), None, _ip(res["status"]), None, None, None,
+                       None, None, None, 0)
+        nm = NmOpts(alpha, beta, gamma, eps, lam, int(iter_max))
+        d = spec.desc()
+        self._check(self.f_nm_fleet(self.ctx, C.byref(d), C.byref(opts), C.byref(nm), P, _dp(x0f), x0.shape[1], _dp(uf), u_count,
+                                    float(kl_bound), _dp(st["theta_high_init"]), _dp(st["theta_low_init"]), _dp(st["c_high"]),
+                                    _dp(st["c_low"]), _ip(st["has_c"]), _dp(res["theta_opt"]), _dp(res["value"]),
+                                    _ip(res["nm_iters"]), _ip(res["n_evals"]), C.byref(out)), "nm_solve_fleet")
+        res["state"] = st
         return res
 
     # device-resident variant (throughput measurement): stage once, run many, fetch

@@ -160,3 +160,14 @@ def solve_(ce, problem, x_0, u_array, rng, verbose=False, serial=False, **kw):
             guard += 1
             if guard > 10000:
                 raise
+
+
+def solve_fleet_(ce, problem, x0, u_init, kl_bound, cost_params=None, rng_seed=0, z_inject=None, want=("x", "l", "L")):
+    """solve! for a FLEET of independent problems in one call (additive API): x0 (n, P), per-problem cost parameter blocks
+    (P, ncp).  The whole CE loop runs on the device (ratilqr_ce_solve_fleet).  Returns a dict of per-problem arrays and
+    updates nothing on `ce` except reading its options (mu_init / sigma_init come back in the dict, per problem)."""
+    ILEQGSolver(problem, **ce.ileqg_kwargs())  # constructor assertions
+    spec = problem.spec(cost_params=cost_params)
+    return ce._be().ce_solve_fleet(spec, x0, u_init, kl_bound, ce.mu_init, ce.sigma_init, num_samples=ce.num_samples,
+                                   num_elite=ce.num_elite, iter_max=ce.iter_max, lam=ce.lam, use_theta_max=ce.use_theta_max,
+                                   z_inject=z_inject, seed=rng_seed, opts=ILEQGSolver(problem, **ce.ileqg_kwargs()).opts(), want=want)

@@ -812,6 +812,73 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   return 0;
 }
 
+// ---- RAT iLQR++ for a fleet of problems (nelder_mead_bilevel_optimization.jl:276-352) -------------------------------
+int32_t ratilqr_nm_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                               const ratilqr_nm_opts* nm, int32_t P, const double* x0, int32_t x0_count,
+                               const double* u_init, int32_t u_count, double kl_bound, double* theta_high_init,
+                               double* theta_low_init, double* c_high, double* c_low, int32_t* has_c, double* theta_opt,
+                               double* value, int32_t* nm_iters, int32_t* n_evals, ratilqr_ileqg_out* final_out) {
+  if (!ctx) return -1;
+  if (!nm || P < 1 || !theta_high_init || !theta_low_init || !c_high || !c_low || !has_c || !theta_opt || !value) FAIL(-1, "bad arguments");
+  if (!(kl_bound >= 0)) FAIL(-3, "KL Divergence Bound must be non-negative");  // :280
+  cudaStream_t st = ctx->stream;
+  rll::NmFleet c;
+  memset(&c, 0, sizeof(c));
+  c.P = P; c.iter_max = nm->iter_max; c.alpha = nm->alpha; c.beta = nm->beta; c.gamma = nm->gamma; c.eps = nm->eps;
+  c.lambda = nm->lambda; c.kl = kl_bound;
+  const size_t Pb = (size_t)P * 8;
+  std::vector<int32_t> ones(P, 1), izeros(P, 0);
+  ratilqr_batch_in in;
+  in.P = P; in.K = 6; in.x0 = x0; in.x0_count = x0_count; in.u_init = u_init; in.u_count = u_count; in.theta = nullptr;
+  int rc = 0;
+  if (kl_bound > 0) { if ((rc = stage_internal(ctx, desc, opts, &in, 0, true))) return rc; }
+  UP(ctx->s[0], theta_high_init, Pb); UP(ctx->s[1], theta_low_init, Pb);   // initialize! :164-168: theta_* <- *_init
+  UP(ctx->s[2], theta_high_init, Pb); UP(ctx->s[3], theta_low_init, Pb);
+  UP(ctx->s[4], c_high, Pb); UP(ctx->s[5], c_low, Pb);
+  CU(ctx->s[6].reserve(Pb)); CU(ctx->s[7].reserve(Pb));
+  UP(ctx->s[8], has_c, (size_t)P * 8); UP(ctx->s[9], izeros.data(), (size_t)P * 4);
+  UP(ctx->s[10], ones.data(), (size_t)P * 4); UP(ctx->s[11], izeros.data(), (size_t)P * 4);
+  UP(ctx->s[12], izeros.data(), (size_t)P * 4); CU(ctx->s[13].reserve(8));
+  c.th_high = ctx->s[0].as<double>(); c.th_low = ctx->s[1].as<double>(); c.th_high_init = ctx->s[2].as<double>();
+  c.th_low_init = ctx->s[3].as<double>(); c.c_high = ctx->s[4].as<double>(); c.c_low = ctx->s[5].as<double>();
+  c.theta_opt = ctx->s[6].as<double>(); c.value_out = ctx->s[7].as<double>(); c.has_c = ctx->s[8].as<int32_t>();
+  c.iter = ctx->s[9].as<int32_t>(); c.active = ctx->s[10].as<int32_t>(); c.evals = ctx->s[11].as<int32_t>();
+  c.phase = ctx->s[12].as<int32_t>(); c.n_active = ctx->s[13].as<int32_t>();
+  int rounds = 0;
+  if (kl_bound > 0) {
+    c.theta = ctx->d_theta.as<double>(); c.value = ctx->sp.value; c.status = ctx->sp.status;
+    ctx->sp.active = c.active;
+    while (true) {
+      rll::launch_nm_candidates(c, st);
+      if ((rc = check_launch(ctx, "k_nm_candidates"))) return rc;
+      if ((rc = run_internal(ctx, 1, nullptr))) return rc;
+      CU(cudaMemsetAsync(c.n_active, 0, 4, st));
+      rll::launch_nm_decide(c, st);
+      if ((rc = check_launch(ctx, "k_nm_decide"))) return rc;
+      int32_t n_active = 0;
+      CU(cudaMemcpyAsync(&n_active, c.n_active, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (n_active == 0) break;
+      if (++rounds > 100000) FAIL(-6, "Nelder-Mead vertex search does not terminate (the reference would spin forever here)");
+    }
+  }
+  in.K = 1;
+  const int fwant = final_out ? ((final_out->x ? 1 : 0) | (final_out->l ? 2 : 0) | (final_out->L ? 4 : 0)) : 0;
+  if ((rc = stage_internal(ctx, desc, opts, &in, 0, true, fwant))) return rc;
+  rll::launch_nm_final(c, ctx->d_theta.as<double>(), nullptr, nullptr, 0, st);
+  if ((rc = check_launch(ctx, "k_nm_final"))) return rc;
+  if ((rc = run_internal(ctx, 1, nullptr))) return rc;
+  rll::launch_nm_final(c, ctx->d_theta.as<double>(), ctx->sp.value, ctx->sp.status, 1, st);
+  if ((rc = check_launch(ctx, "k_nm_final"))) return rc;
+  DOWNSYNC(theta_opt, c.theta_opt, Pb); DOWNSYNC(value, c.value_out, Pb);
+  DOWNSYNC(theta_high_init, c.th_high_init, Pb); DOWNSYNC(theta_low_init, c.th_low_init, Pb);
+  DOWNSYNC(c_high, c.c_high, Pb); DOWNSYNC(c_low, c.c_low, Pb); DOWNSYNC(has_c, c.has_c, (size_t)P * 8);
+  DOWNSYNC(nm_iters, c.iter, (size_t)P * 4); DOWNSYNC(n_evals, c.evals, (size_t)P * 4);
+  CU(cudaStreamSynchronize(st));
+  if (final_out) return fetch_internal(ctx, final_out);
+  return 0;
+}
+
 int32_t ratilqr_fp64_peak_probe(ratilqr_ctx* ctx, double* tflops, float* ms) {
   if (!ctx) return -1;
   CU(cudaSetDevice(ctx->device));

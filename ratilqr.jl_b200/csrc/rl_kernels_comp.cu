@@ -445,6 +445,106 @@ __global__ void k_ce_final_update(CeFleet c, double* theta_final, const double* 
   }
 }
 
+// ---- RAT iLQR++ fleet kernels (thread = problem) ---------------------------------------------------------------
+// candidate slots per problem: phase 0 -> [theta_high, theta_low, -, -, -, -]; phase 1 -> [r, e, c1, c2, s1, s2]
+__global__ void k_nm_candidates(NmFleet c) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= c.P || !c.active[p]) return;
+  double* th = c.theta + (size_t)p * 6;
+  if (c.phase[p] == 0) {
+    th[0] = c.th_high[p]; th[1] = c.th_low[p];
+    for (int i = 2; i < 6; ++i) th[i] = th[1];  // unused slots repeat a cheap, valid theta
+    return;
+  }
+  if (c.c_high[p] < c.c_low[p]) {  // step! :184-187
+    double t = c.th_low[p]; c.th_low[p] = c.th_high[p]; c.th_high[p] = t;
+    t = c.c_low[p]; c.c_low[p] = c.c_high[p]; c.c_high[p] = t;
+  }
+  const double lo = c.th_low_init[p], m_ = c.th_low[p], hi = c.th_high[p];
+  const double r = fmax(lo, m_ + c.alpha * (m_ - hi));          // :195-196
+  th[0] = r;
+  th[1] = fmax(lo, m_ + c.beta * (r - m_));                     // expansion :204-205
+  th[2] = fmax(lo, m_ + c.gamma * (r - m_));                    // contraction if theta_high <- theta_r (:228-233)
+  th[3] = fmax(lo, m_ + c.gamma * (hi - m_));                   // contraction if theta_high kept
+  th[4] = (r + m_) / 2;                                         // shrink points :239
+  th[5] = (hi + m_) / 2;
+}
+
+__global__ void k_nm_decide(NmFleet c) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= c.P || !c.active[p]) return;
+  const double* th = c.theta + (size_t)p * 6;
+  const double* val = c.value + (size_t)p * 6;
+  const int32_t* st = c.status + (size_t)p * 6;
+  auto cost = [&](int i) { return st[i] == 0 ? val[i] + c.kl / th[i] : HUGE_VAL; };  // compute_cost_worker :134-158
+  if (c.phase[p] == 0) {  // solve! :283-304: find finite vertex costs, halving theta (and the persistent *_init) on Inf
+    bool done = true;
+    if (!c.has_c[2 * p]) {
+      double ch = cost(0);
+      c.evals[p] += 1;
+      if (ch == HUGE_VAL) { c.th_high[p] *= c.lambda; c.th_high_init[p] *= c.lambda; done = false; }
+      else { c.c_high[p] = ch; c.has_c[2 * p] = 1; }
+    }
+    if (!c.has_c[2 * p + 1]) {
+      // the reference evaluates c_low only after c_high is finite; evaluations are pure, so using the speculative
+      // result is equivalent -- but the evaluation COUNT follows the reference: count it once c_high is known
+      double cl = cost(1);
+      if (c.has_c[2 * p]) {
+        c.evals[p] += 1;
+        if (cl == HUGE_VAL) { c.th_low[p] *= c.lambda; c.th_low_init[p] *= c.lambda; done = false; }
+        else { c.c_low[p] = cl; c.has_c[2 * p + 1] = 1; }
+      } else done = false;
+    }
+    if (done) c.phase[p] = 1;
+    atomicAdd(c.n_active, 1);
+    return;
+  }
+  // step! :174-252, replayed on the speculative results
+  c.iter[p] += 1;
+  const double c_r = cost(0);
+  c.evals[p] += 1;
+  if (c_r < c.c_low[p]) {
+    const double c_e = cost(1);
+    c.evals[p] += 1;
+    if (c_e < c_r) { c.th_high[p] = th[1]; c.c_high[p] = c_e; } else { c.th_high[p] = th[0]; c.c_high[p] = c_r; }
+  } else {
+    bool moved = false;
+    if (c_r < c.c_high[p]) { c.th_high[p] = th[0]; c.c_high[p] = c_r; moved = true; }
+    const int ic = moved ? 2 : 3;
+    const double c_c = cost(ic);
+    c.evals[p] += 1;
+    if (c_c > c.c_high[p]) {
+      const int is = moved ? 4 : 5;
+      c.th_high[p] = th[is];            // (theta_high + theta_low)/2 :239
+      c.c_high[p] = cost(is);
+      c.evals[p] += 1;
+    } else { c.th_high[p] = th[ic]; c.c_high[p] = c_c; }
+  }
+  const double c_mean = (c.c_low[p] + c.c_high[p]) / 2;  // :309-310
+  const double d1 = c.c_high[p] - c_mean, d2 = c.c_low[p] - c_mean;
+  const double stdev = sqrt(0.5 * (d1 * d1 + d2 * d2));
+  if (stdev < c.eps || c.iter[p] == c.iter_max) c.active[p] = 0;
+  else atomicAdd(c.n_active, 1);
+}
+
+// stage 0: theta_final <- theta_low (or 0 if kl == 0), all problems active; stage 1: collect the final solve (no retry, :334-350)
+__global__ void k_nm_final(NmFleet c, double* theta_final, const double* value, const int32_t* status, int stage) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= c.P) return;
+  if (stage == 0) {
+    double t = c.kl > 0 ? c.th_low[p] : 0.0;  // :325 / :332
+    theta_final[p] = t; c.theta_opt[p] = t; c.active[p] = 1;
+  } else {
+    c.value_out[p] = status[p] == 0 ? (c.kl > 0 ? value[p] + c.kl / theta_final[p] : value[p]) : HUGE_VAL;
+  }
+}
+
+void launch_nm_candidates(const NmFleet& c, cudaStream_t st) { k_nm_candidates<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c); }
+void launch_nm_decide(const NmFleet& c, cudaStream_t st) { k_nm_decide<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c); }
+void launch_nm_final(const NmFleet& c, double* tf, const double* v, const int32_t* s, int stage, cudaStream_t st) {
+  k_nm_final<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c, tf, v, s, stage);
+}
+
 void launch_ce_draw(const CeFleet& c, cudaStream_t st) { k_ce_draw<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c); }
 void launch_ce_update(const CeFleet& c, cudaStream_t st) { k_ce_update<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c); }
 void launch_ce_pick_theta(const CeFleet& c, double* tf, cudaStream_t st) { k_ce_pick_theta<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c, tf); }

@@ -102,6 +102,20 @@ void launch_ce_update(const CeFleet& c, cudaStream_t st);
 void launch_ce_pick_theta(const CeFleet& c, double* theta_final, cudaStream_t st);
 void launch_ce_final_update(const CeFleet& c, double* theta_final, const double* value, const int32_t* status, cudaStream_t st);
 
+// ---- RAT iLQR++ (Nelder-Mead over theta) for a fleet ------------------------------------------------------------
+struct NmFleet {
+  int P, iter_max;
+  double alpha, beta, gamma, eps, lambda, kl;
+  double *th_high, *th_low, *th_high_init, *th_low_init, *c_high, *c_low, *theta_opt, *value_out;
+  int32_t *has_c /* 2 per problem */, *iter, *active, *evals, *phase /* 0 = initial vertices, 1 = stepping */;
+  double* theta;                               // P*6 candidate slots consumed by the solve kernel
+  const double* value; const int32_t* status;  // its results
+  int32_t* n_active;
+};
+void launch_nm_candidates(const NmFleet& c, cudaStream_t st);
+void launch_nm_decide(const NmFleet& c, cudaStream_t st);
+void launch_nm_final(const NmFleet& c, double* theta_final, const double* value, const int32_t* status, int stage, cudaStream_t st);
+
 // DFMA throughput probe: returns total flops issued
 double launch_fp64_probe(double* sink, int iters, cudaStream_t st);
 

@@ -146,3 +146,13 @@ def solve_(nm, problem, x_0, u_array, verbose=False, **kw):
     if kl_bound > 0:
         return theta_opt, x_array, l_array, L_array, value + kl_bound / theta_opt
     return theta_opt, x_array, l_array, L_array, value
+
+
+def solve_fleet_(nm, problem, x0, u_init, kl_bound, cost_params=None, state=None, want=("x", "l", "L")):
+    """solve! for a FLEET of independent problems in one call (additive API, ratilqr_nm_solve_fleet): the six candidate
+    theta of every problem's step are solved in one launch and the decision tree is replayed per problem on the device.
+    `state` (from a previous call's result) carries theta_*_init and the vertex costs across calls."""
+    spec = problem.spec(cost_params=cost_params)
+    return nm._be().nm_solve_fleet(spec, x0, u_init, kl_bound, state=state, alpha=nm.alpha, beta=nm.beta, gamma=nm.gamma,
+                                   eps=nm.eps, lam=nm.lam, iter_max=nm.iter_max, theta_high_init=nm.theta_high_init,
+                                   theta_low_init=nm.theta_low_init, opts=ILEQGSolver(problem, **nm.ileqg_kwargs()).opts(), want=want)

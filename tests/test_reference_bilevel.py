@@ -187,3 +187,37 @@ def test_ce_fleet_on_device_matches_oracle_per_problem(gpu_be, oracle_be, kl, mu
         if kl > 0:
             assert np.isclose(g["mu"][p], mu, rtol=1e-9) and np.isclose(g["sigma"][p], sigma, rtol=1e-9)
         assert np.allclose(g["x"][..., p], x, rtol=1e-9, atol=1e-12) and np.allclose(g["L"][..., p], L, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_nm_fleet_on_device_matches_oracle_per_problem(gpu_be, oracle_be):
+    """ratilqr_nm_solve_fleet (RAT iLQR++ for P problems in lock-step, speculative candidates) vs P independent runs of the
+    oracle's restatement of solve!, including the persistence of the vertex costs across a second call."""
+    P = 7
+    prob, cps, x0, u = wl.fleet(P, N=20)
+    spec = prob.spec(cost_params=cps)
+    kw = dict(eps=1e-3, iter_max=12, theta_high_init=300.0, theta_low_init=1e-8)  # 300: infeasible => theta_high halves first
+    g1 = gpu_be.nm_solve_fleet(spec, x0, u, 0.5, **kw)
+    g2 = gpu_be.nm_solve_fleet(spec, x0, u, 0.5, state=g1["state"], **kw)
+    f = oracle_be.raw.oracle_nm_solve
+    f.restype = C.c_int32
+    n, m, N = spec.n, spec.m, spec.N
+    opts = make_opts()
+    uflat = np.ascontiguousarray(u.ravel(order="F"))
+    for p in range(P):
+        sp = prob.spec(cost_params=cps[p])
+        d = sp.desc()
+        o = OracleNMOpts(1.0, 2.0, 0.5, 1e-3, 0.5, 12, 300.0, 1e-8, 0.0, 0.0, 0, 0)
+        x0p = np.ascontiguousarray(x0[:, p])
+        for g in (g1, g2):
+            th, val = C.c_double(), C.c_double()
+            it, ev, st = C.c_int32(), C.c_int32(), C.c_int32()
+            x = np.zeros((n, N + 1), order="F"); l = np.zeros((m, N), order="F"); L = np.zeros((m, n, N), order="F")
+            rc = f(C.byref(d), C.byref(opts), C.byref(o), x0p.ctypes.data_as(dp), uflat.ctypes.data_as(dp), C.c_double(0.5),
+                   C.byref(th), C.byref(val), C.byref(it), C.byref(ev), x.ctypes.data_as(dp), l.ctypes.data_as(dp),
+                   L.ctypes.data_as(dp), C.byref(st))
+            assert rc == 0 and st.value == g["status"][p] == 0
+            assert g["nm_iters"][p] == it.value and g["n_evals"][p] == ev.value, (p, g["nm_iters"][p], it.value, g["n_evals"][p], ev.value)
+            assert np.isclose(g["theta_opt"][p], th.value, rtol=1e-12) and np.isclose(g["value"][p], val.value, rtol=1e-9)
+            assert np.isclose(g["state"]["theta_high_init"][p], o.theta_high_init) and np.isclose(g["state"]["c_low"][p], o.c_low, rtol=1e-9)
+            assert np.allclose(g["x"][..., p], x, rtol=1e-9, atol=1e-12) and np.allclose(g["L"][..., p], L, rtol=1e-9, atol=1e-12)
