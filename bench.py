@@ -7,7 +7,7 @@
 Workload (config.workload = "c2_fleet"): BASELINE.json configs[1] -- 4-state unicycle, T=50, 1024 theta
 samples per problem -- replicated over P independent problems per GPU (x0 and goal drawn per problem, as
 in configs[4]) so that one step fills the device: 444 x 1024 = 454,656 iLEQG solves = eight full waves of
-148 SMs x 384 resident instances (12 warps/SM at 168 registers).  A "step" = one batched solve of all
+148 SMs x 384 resident instances (12 warps/SM at 168 registers, 128-thread CTAs).  A "step" = one batched solve of all
 instances (one launch of the persistent solve kernel).
 Weak scaling: every rank owns P problems; there is no data-path collective (instances are independent).
 

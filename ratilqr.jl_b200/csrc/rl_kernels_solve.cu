@@ -81,7 +81,10 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
       case 7: launch_shape<D, CT, 32, 14>(P, st); return;   // 144 regs
       case 8: launch_shape<D, CT, 32, 13>(P, st); return;   // 152 regs
       case 9: launch_shape<D, CT, 32, 10>(P, st); return;   // 200 regs
-      default: launch_shape<D, CT, 64, 6>(P, st); return;    // best of the sweep in profiles/r01_tune_*.jsonl
+      case 10: launch_shape<D, CT, 64, 7>(P, st); return;   // 144 regs, 14 warps/SM
+      case 11: launch_shape<D, CT, 128, 3>(P, st); return;  // 168 regs, 128-thread CTAs
+      case 12: launch_shape<D, CT, 64, 5>(P, st); return;   // 200 regs, 10 warps/SM
+      default: launch_shape<D, CT, 128, 3>(P, st); return;   // best of the sweeps in profiles/r01_tune_*.jsonl
     }
   } else {
     launch_shape<D, CT, 64, 4>(P, st);
