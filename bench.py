@@ -244,6 +244,7 @@ def main():
     out = None
     if rank == 0:
         peak_tf = be.fp64_probe()
+        peak_sus = be.fp64_probe_sustained(1.0)
         ach_tf = flops / (ms_per_step * 1e-3) / 1e12
         peaks = {}
         try:
@@ -274,7 +275,8 @@ def main():
                        "api": "ratilqr_ce_costs (compute_cost), host buffers in, cost+status vectors out"},
                "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                             "traffic": traffic, "algorithmic_bytes_per_launch": byts, "kernel": "k_ileqg_solve<unicycle, quadratic>",
-                            "peak_source": "DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 figure)",
+                            "peak_source": "burst DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 figure)",
+                            "peak_sustained": peak_sus, "frac_of_sustained": ach_tf / peak_sus,
                             "flops_per_launch": flops},
                "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},

@@ -255,6 +255,8 @@ int32_t ratilqr_pets_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc,
 /* ---- measurement utilities --------------------------------------------------------- */
 /* dependent-chain-free DFMA loop on every SM: returns achieved TFLOP/s (FP64, non-tensor) */
 int32_t ratilqr_fp64_peak_probe(ratilqr_ctx* ctx, double* tflops, float* ms);
+/* same loop launched back to back for `seconds` (power-capped steady state): the sustained FP64 figure */
+int32_t ratilqr_fp64_peak_probe_sustained(ratilqr_ctx* ctx, double seconds, double* tflops);
 /* number of kernel launches issued by this ctx since creation */
 int64_t ratilqr_launch_count(const ratilqr_ctx* ctx);
 

@@ -175,6 +175,7 @@ class CApi:
         self.f_run = self._fn("ileqg_run", [vp, i32, C.POINTER(C.c_float)])
         self.f_fetch = self._fn("ileqg_fetch", [vp, OUT])
         self.f_probe = self._fn("fp64_peak_probe", [vp, dp, C.POINTER(C.c_float)])
+        self.f_probe_sus = self._fn("fp64_peak_probe_sustained", [vp, f64, dp])
         self.f_launches = self._fn("launch_count", [vp], restype=C.c_int64)
         self.f_pets_solve = self._fn("pets_solve", [vp, PD, GD, dp, i32, i32, i32, i32, f64, dp, dp, C.c_uint64, dp, dp])
 
@@ -348,6 +349,12 @@ class CApi:
         """measured non-tensor FP64 FMA throughput of this device in TFLOP/s"""
         tf, ms = C.c_double(0.0), C.c_float(0.0)
         self._check(self.f_probe(self.ctx, C.byref(tf), C.byref(ms)), "fp64_peak_probe")
+        return float(tf.value)
+
+    def fp64_probe_sustained(self, seconds=1.0):
+        """DFMA throughput in TFLOP/s over the second half of a `seconds`-long back-to-back run (power-capped clocks)"""
+        tf = C.c_double(0.0)
+        self._check(self.f_probe_sus(self.ctx, float(seconds), C.byref(tf)), "fp64_peak_probe_sustained")
         return float(tf.value)
 
     def launch_count(self):

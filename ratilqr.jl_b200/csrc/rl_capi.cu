@@ -902,4 +902,25 @@ int32_t ratilqr_fp64_peak_probe(ratilqr_ctx* ctx, double* tflops, float* ms) {
   return 0;
 }
 
+int32_t ratilqr_fp64_peak_probe_sustained(ratilqr_ctx* ctx, double seconds, double* tflops) {
+  if (!ctx) return -1;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->s[0].reserve(64));
+  const int iters = 1 << 16;
+  double flops = rll::launch_fp64_probe(ctx->s[0].as<double>(), iters, ctx->stream);
+  CU(cudaStreamSynchronize(ctx->stream));
+  // time the second half of the run only (clocks have settled under the power cap by then)
+  const int n_launch = (int)(seconds / 0.0092) + 2, half = n_launch / 2;
+  for (int i = 0; i < half; ++i) rll::launch_fp64_probe(ctx->s[0].as<double>(), iters, ctx->stream);
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int i = half; i < n_launch; ++i) rll::launch_fp64_probe(ctx->s[0].as<double>(), iters, ctx->stream);
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(cudaEventSynchronize(ctx->ev1));
+  float t = 0;
+  CU(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+  if (int rc = check_launch(ctx, "k_fp64_probe", n_launch + 1)) return rc;
+  if (tflops) *tflops = flops * (n_launch - half) / (t * 1e-3) / 1e12;
+  return 0;
+}
+
 }  // extern "C"
