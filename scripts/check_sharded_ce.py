@@ -1,0 +1,39 @@
+"""2-GPU (or N-GPU) check of the single-population sharding: every rank solves a block of the theta samples on
+its own GPU, ONE all_gather of the cost vector over NCCL, and every rank must hold exactly the single-GPU result.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/check_sharded_ce.py"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ratilqr_b200 as R  # noqa: E402
+from ratilqr_b200 import distributed as D  # noqa: E402
+from ratilqr_b200 import workloads as wl  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+be = R.new_backend(local)
+prob, x0, u = wl.c2_problem()
+spec = prob.spec()
+theta = wl.c2_thetas(1024)
+full = D.sharded_ce_costs(be, spec, x0, u, theta, 0.1)  # warm-up + result
+dist.barrier(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+full = D.sharded_ce_costs(be, spec, x0, u, theta, 0.1)
+dist.barrier(); torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+single = be.ce_costs(spec, x0, u, theta, 0.1)[0]
+ok = bool(np.array_equal(full, single))
+flags = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(json.dumps({"check": "sharded_ce_costs over NCCL", "world": world, "thetas": 1024, "identical_on_all_ranks": bool(flags.item() == 1.0),
+                      "ms_sharded": dt * 1e3, "elite_theta": float(theta[np.argsort(full, kind="stable")[0]])}))
+dist.destroy_process_group()
+be.close()
