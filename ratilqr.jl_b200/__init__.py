@@ -3,7 +3,7 @@
 Export list mirrors src/RATiLQR.jl:20-74 (Julia `f!` -> `f_`; per-solver functions live in their
 modules because Python has no multiple dispatch: `ileqg.solve_`, `cross_entropy.solve_`, ...).
 """
-from . import cross_entropy, ileqg, models, nelder_mead, pets  # noqa: F401
+from . import cross_entropy, ileqg, models, mpc, nelder_mead, pets  # noqa: F401
 from ._capi import ApiError, Spec, make_opts  # noqa: F401
 from ._lib import default_backend, load_library, new_backend, set_default_backend  # noqa: F401
 from .cross_entropy import CrossEntropyBilevelOptimizationSolver, InjectedNormals  # noqa: F401

@@ -221,3 +221,18 @@ def test_nm_fleet_on_device_matches_oracle_per_problem(gpu_be, oracle_be):
             assert np.isclose(g["theta_opt"][p], th.value, rtol=1e-12) and np.isclose(g["value"][p], val.value, rtol=1e-9)
             assert np.isclose(g["state"]["theta_high_init"][p], o.theta_high_init) and np.isclose(g["state"]["c_low"][p], o.c_low, rtol=1e-9)
             assert np.allclose(g["x"][..., p], x, rtol=1e-9, atol=1e-12) and np.allclose(g["L"][..., p], L, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_fleet_mpc_drives_every_system_to_its_goal(gpu_be):
+    """receding-horizon RAT iLQR for a small fleet: warm-started plans, persisted CE state, noisy true system"""
+    from ratilqr_b200.mpc import run_fleet_mpc
+    P = 12
+    prob, cps, x0, u = wl.fleet(P, N=20)
+    out = run_fleet_mpc(gpu_be, prob, cps, x0, steps=45, kl_bound=0.1, rng=np.random.default_rng(3))
+    goals = cps[:, 5:7]                                   # xg(0:2) of every problem's cost block
+    d0 = np.linalg.norm(x0[:2].T - goals, axis=1)
+    d1 = np.linalg.norm(out["x"][:2, -1].T - goals, axis=1)
+    assert np.all(d1 < 0.35 * d0) and np.all(np.isfinite(out["value"]))  # every vehicle closed most of its distance
+    assert np.all(out["theta"] > 0) and np.all(out["mu_init"] > 0)
+    assert np.median(out["ms"][5:]) < np.median(out["ms"][:3]) * 1.5     # warm starts do not make steps slower
