@@ -120,6 +120,17 @@ static int launch_coop_one(const SolveParams& P, double* traj_global, bool query
   using CT = Cost<CID, D::n, D::m>;
   size_t smem = coop_smem_bytes<D, CT>(P.N, true);
   bool in_smem = smem <= 200 * 1024;
+  if (in_smem && !query_only && traj_global) {
+    // Trajectories in shared memory minimise latency, but cap residency (5 warps/SM for the quadrotor).  When the batch
+    // exceeds one resident wave, keep only the per-stage matrices in shared memory and the trajectories in HBM
+    // (contiguous per instance, read once per stage): ~3x more resident warps to hide the shared-memory latency chains.
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t per_sm = (227 * 1024) / (smem + 1024);
+    const char* e = getenv("RATILQR_COOP_TRAJ");  // smem / global: force (tuning)
+    if (e ? (e[0] == 'g') : ((size_t)P.B > per_sm * (size_t)sms)) in_smem = false;
+  }
   if (!in_smem) smem = coop_smem_bytes<D, CT>(P.N, false);
   if (smem_out) *smem_out = smem;
   if (query_only) return 0;

@@ -66,6 +66,19 @@ if "c3" in which:  # RAT iLQR++ (Nelder-Mead) on the 12-state quadrotor, T = 40
                       "mc256_mean_var_risk": mc["stats"][0].tolist(),
                       "note": "thread-per-instance kernel runs n=12 from local memory; CTA-per-instance kernel is next"}))
 
+if "c3_fleet" in which:  # batched quadrotor iLEQG solves (warp-cooperative kernel) vs the CPU oracle
+    prob, x0, u = wl.c3_problem()
+    spec = prob.spec()
+    for B in (6, 740, 4096):
+        th = np.concatenate([[0.0], wl.positive_thetas(B - 1, mu=0.02, sigma=0.02, key=B)])
+        tg = timed(lambda: be.ce_costs(spec, x0, u, th, 0.1), 2)
+        cost, st = be.ce_costs(spec, x0, u, th, 0.1)
+        Bc = min(B, 64)
+        tc = timed(lambda: o.ce_costs(spec, x0, u, th[:Bc], 0.1), 1)
+        print(json.dumps({"config": f"C3 quadrotor n=12 m=4 T=40, {B} iLEQG solves in one call (coop kernel)", "gpu_ms": tg * 1e3,
+                          "gpu_solves_per_s": B / tg, "feasible": int((st == 0).sum()), "cpu_oracle_solves_per_s": Bc / tc,
+                          "cpu_cores": cores, "cpu_sample": Bc}))
+
 if "c4" in which:  # PETS CEM on cart-pole: 4096 sequences x (5-model ensemble x 30 particles), T = 30, 5 iterations
     prob, x0 = wl.c4_problem()
     spec, gen = prob.spec(), prob.f_stochastic.gen()
