@@ -6,9 +6,9 @@
 
 Workload (config.workload = "c2_fleet"): BASELINE.json configs[1] -- 4-state unicycle, T=50, 1024 theta
 samples per problem -- replicated over P independent problems per GPU (x0 and goal drawn per problem, as
-in configs[4]) so that one step fills the device: 444 x 1024 = 454,656 iLEQG solves = eight full waves of
-148 SMs x 384 resident instances (12 warps/SM at 168 registers, 128-thread CTAs).  A "step" = one batched solve of all
-instances (one launch of the persistent solve kernel).
+in configs[4]) so that one step fills the device: 1776 x 1024 = 1,818,624 iLEQG solves = 32 full waves of
+148 SMs x 384 resident instances (12 warps/SM at 168 registers, 128-thread CTAs; 16 GB of SoA workspace).  A "step" =
+one batched solve of all instances (one launch of the persistent solve kernel).  (--problems 444 = 8 waves: -8 %.)
 Weak scaling: every rank owns P problems; there is no data-path collective (instances are independent).
 
 value  : solves/s, kernel only, inputs resident in HBM, CUDA events on the library's stream.
@@ -130,7 +130,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--problems", type=int, default=444, help="independent unicycle problems per GPU (x 1024 theta each)")
+    ap.add_argument("--problems", type=int, default=1776, help="independent unicycle problems per GPU (x 1024 theta each)")
     ap.add_argument("--fleet-problems", type=int, default=8192, help="RAT iLQR problems per GPU for the MPC-step figure")
     ap.add_argument("--cpu-sample-problems", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
