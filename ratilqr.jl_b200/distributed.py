@@ -29,14 +29,56 @@ def sharded_ce_costs(be, spec, x0, u_init, theta, kl_bound, opts=None, group=Non
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = block_range(theta.size, rank, world)
     local = be.ce_costs(spec, x0, u_init, theta[lo:hi], kl_bound, opts=opts)[0] if hi > lo else np.zeros(0)
+    return _all_gather_blocks(local, theta.size, group)  # num_samples doubles: latency-bound on NVLink 5 / NVSwitch
+
+
+def _all_gather_blocks(local, count, group):
+    """all_gather of a block-partitioned float64 vector; every rank returns the full vector of `count` entries"""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [block_range(count, r, world) for r in range(world)]
+    lo, hi = sizes[rank]
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    sizes = [block_range(theta.size, r, world) for r in range(world)]
     width = max(h - l for l, h in sizes)
     buf = torch.full((width,), float("nan"), dtype=torch.float64, device=dev)
-    buf[: hi - lo] = torch.from_numpy(local).to(dev)
+    if hi > lo:
+        buf[: hi - lo] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(dev)
     out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf, group=group)  # num_samples doubles: latency-bound on NVLink 5 / NVSwitch
+    dist.all_gather(out, buf, group=group)
     return np.concatenate([o[: h - l].cpu().numpy() for o, (l, h) in zip(out, sizes)])
+
+
+def sharded_pets_costs(be, spec, gen, x0, controls, particles, noise=None, seed=0, group=None):
+    """PETS compute_cost (pets.jl:100-126) with the action sequences block-partitioned over the ranks of `group`
+    and ONE all_gather of the cost vector (the analogue of the reference's per-worker `remotecall_fetch`,
+    pets.jl:108-125).  `controls` (m, N, C) and, when given, `noise` (n, N, particles, C) are replicated inputs;
+    each rank rolls out its own block of sequences.  With injected noise the result equals the one-process result
+    bit for bit; with on-device Philox each rank draws from the stream `seed + rank` (statistical equivalence,
+    like the reference's `randjump` streams)."""
+    import torch.distributed as dist
+    controls = np.asarray(controls, dtype=np.float64)
+    Cn = controls.shape[2]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return be.pets_costs(spec, x0, controls, particles, noise=noise, seed=seed, gen=gen)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = block_range(Cn, rank, world)
+    local = np.zeros(0)
+    if hi > lo:
+        nz = None if noise is None else np.asarray(noise, dtype=np.float64)[..., lo:hi]
+        local = be.pets_costs(spec, x0, controls[:, :, lo:hi], particles, noise=nz, seed=seed + rank, gen=gen)
+    return _all_gather_blocks(local, Cn, group)
+
+
+def sharded_pets_step(be, spec, gen, x0, mu, Sigma, controls, particles, num_elite, smoothing, noise=None, seed=0,
+                      group=None):
+    """one PETS CEM iteration (pets.jl:193-245) over a replicated population `controls` (m, N, C): sharded rollouts,
+    all_gather of the costs, then the stable top-k elite selection + smoothed refit run redundantly and
+    deterministically on every rank (ties broken by global index, pets.jl:167), so (mu, Sigma) stay replicated
+    without a broadcast.  Returns (mu, Sigma, elite_idx, cost)."""
+    cost = sharded_pets_costs(be, spec, gen, x0, controls, particles, noise=noise, seed=seed, group=group)
+    mu_n, Sg_n, idx = be.pets_refit(controls, cost, num_elite, smoothing, mu, Sigma)
+    return mu_n, Sg_n, idx, cost
 
 
 def fleet_block(P, rank, world):

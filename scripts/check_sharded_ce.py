@@ -35,5 +35,28 @@ dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(json.dumps({"check": "sharded_ce_costs over NCCL", "world": world, "thetas": 1024, "identical_on_all_ranks": bool(flags.item() == 1.0),
                       "ms_sharded": dt * 1e3, "elite_theta": float(theta[np.argsort(full, kind="stable")[0]])}))
+
+# ---- PETS (configs[3]): action sequences sharded, injected noise => bit-identical costs + redundant refit
+pprob, px0 = wl.c4_problem()
+pspec, gen = pprob.spec(), pprob.f_stochastic.gen()
+rng = np.random.default_rng(3)
+C_, Kp, N_ = 1024, 30, pspec.N
+controls = rng.standard_normal((1, N_, C_))
+noise = 1e-2 * rng.standard_normal((4, N_, Kp, C_))
+mu, Sg = np.zeros((1, N_)), np.ones((1, 1, N_))
+D.sharded_pets_step(be, pspec, gen, px0, mu, Sg, controls, Kp, 102, 0.1, noise=noise)
+dist.barrier(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+mu_n, Sg_n, idx, cost = D.sharded_pets_step(be, pspec, gen, px0, mu, Sg, controls, Kp, 102, 0.1, noise=noise)
+dist.barrier(); torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+cost1 = be.pets_costs(pspec, px0, controls, Kp, noise=noise, gen=gen)
+mu1, Sg1, idx1 = be.pets_refit(controls, cost1, 102, 0.1, mu, Sg)
+ok = bool(np.array_equal(cost, cost1) and np.array_equal(idx, idx1) and np.array_equal(mu_n, mu1) and np.array_equal(Sg_n, Sg1))
+flags = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(json.dumps({"check": "sharded_pets_step over NCCL", "world": world, "sequences": C_, "particles": Kp,
+                      "identical_on_all_ranks": bool(flags.item() == 1.0), "ms_sharded": dt * 1e3}))
 dist.destroy_process_group()
 be.close()

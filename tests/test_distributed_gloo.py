@@ -59,6 +59,57 @@ def test_sharded_ce_costs_world2():
     assert blocks[0] == (0, 3) and blocks[1] == (3, 7)  # fleet partition covers all problems exactly once
 
 
+def _pets_inputs():
+    from ratilqr_b200 import workloads as wl
+    prob, x0 = wl.c4_problem(N=8)
+    rng = np.random.default_rng(11)
+    C_, Kp = 11, 10  # 11: uneven split across 2 ranks; 10 particles = 2 per ensemble member
+    controls = rng.standard_normal((1, 8, C_))
+    noise = 1e-2 * rng.standard_normal((4, 8, Kp, C_))
+    mu, Sg = np.zeros((1, 8)), np.ones((1, 1, 8))
+    return prob, x0, controls, noise, mu, Sg, Kp
+
+
+def _pets_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    import oracle
+    from ratilqr_b200 import distributed as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    be = oracle.load()
+    be.raw.oracle_set_threads(1)
+    prob, x0, controls, noise, mu, Sg, Kp = _pets_inputs()
+    out = D.sharded_pets_step(be, prob.spec(), prob.f_stochastic.gen(), x0, mu, Sg, controls, Kp, 3, 0.1, noise=noise)
+    q.put((rank,) + tuple(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_pets_step_world2():
+    """action sequences sharded over 2 ranks + all_gather of the cost vector + redundant refit == one process"""
+    sys.path.insert(0, ROOT)
+    import oracle
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pets_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    be = oracle.load()
+    prob, x0, controls, noise, mu, Sg, Kp = _pets_inputs()
+    cost = be.pets_costs(prob.spec(), x0, controls, Kp, noise=noise, gen=prob.f_stochastic.gen())
+    mu_r, Sg_r, idx_r = be.pets_refit(controls, cost, 3, 0.1, mu, Sg)
+    assert np.all(np.isfinite(cost))
+    for rank, mu_n, Sg_n, idx, c in got:
+        assert np.array_equal(c, cost) and np.array_equal(idx, idx_r)
+        assert np.array_equal(mu_n, mu_r) and np.array_equal(Sg_n, Sg_r)
+
+
 def test_block_range_partition():
     sys.path.insert(0, ROOT)
     from ratilqr_b200.distributed import block_range
