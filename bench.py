@@ -240,6 +240,17 @@ def main():
     barrier()
     fleet_s = max_over_ranks(time.perf_counter() - t0)
     fleet_ok = sum_over_ranks(float((fr["status"] == 0).sum()))
+    # configs[4] "256 MC samples each": noisy closed-loop rollouts of every problem's optimised policy (Philox noise
+    # coloured with chol(W)), host policy buffers in, J + per-problem statistics out
+    MC = 256
+    fr2 = be.ce_solve_fleet(fspec, fx0, fu, 0.1, 1.0, 2.0, seed=7 + rank, want=("x", "l", "L"))
+    be.mc_rollout(fspec, fr2["x"], fr2["l"], fr2["L"], MC, seed=11 + rank, P=Pf)  # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    mc = be.mc_rollout(fspec, fr2["x"], fr2["l"], fr2["L"], MC, seed=11 + rank, P=Pf)
+    barrier()
+    mc_s = max_over_ranks(time.perf_counter() - t0)
+    mc_finite = sum_over_ranks(float(np.isfinite(mc["stats"][:, 0]).sum()))
 
     out = None
     if rank == 0:
@@ -286,7 +297,10 @@ def main():
                                         "iterations + final solve), ratilqr_ce_solve_fleet, host buffers in, theta_opt/value/l out",
                             "ms_per_fleet_step": fleet_s * 1e3, "problems_per_sec": Pf * world / fleet_s,
                             "us_per_problem_step": fleet_s * 1e6 / (Pf * world), "ce_rounds": fr["rounds"],
-                            "final_solves_ok": int(fleet_ok), "problems": Pf * world}}
+                            "final_solves_ok": int(fleet_ok), "problems": Pf * world,
+                            "mc_eval": {"samples_per_problem": MC, "ms": mc_s * 1e3, "rollouts_per_sec": MC * Pf * world / mc_s,
+                                        "problems_with_finite_mean": int(mc_finite),
+                                        "call": "ratilqr_mc_rollout, host policy buffers in, J + stats out, Philox noise"}}}
         if not args.no_cpu_baseline:
             v, cores, dt = cpu_arm(lambda PP: build_inputs(PP, 0), args.cpu_sample_problems, 1, 0)
             out["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",

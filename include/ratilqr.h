@@ -24,7 +24,9 @@
 #ifndef RATILQR_H
 #define RATILQR_H
 
+#ifndef __CUDACC_RTC__ /* NVRTC: the fixed-width types come from rl_core.cuh */
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -251,6 +253,42 @@ int32_t ratilqr_pets_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc,
                            int32_t C, int32_t particles, int32_t num_elite, int32_t iter_max,
                            double smoothing, const double* z_inject, const double* noise,
                            uint64_t seed, double* mu, double* Sigma);
+
+/* ---- user-extensible device models ---------------------------------
+ * The reference takes arbitrary Julia closures for f, c, h and differentiates them with
+ * ForwardDiff (src/ileqg.jl:265-273: cx, cxx, cu, cuu, cux, fx, fu).  The device analogue: a
+ * CUDA C++ snippet that defines the model once as a template over the scalar type,
+ *   dynamics_src:  template <class T> void dynamics(const double* p, const T* x, const T* u, T* xn);
+ *   cost_src:      template <class T> T stage_cost(const double* cp, int k, const T* x, const T* u);
+ *                  template <class T> T terminal_cost(const double* cp, const T* x);
+ * (k 0-based as in optimal_control_problems.jl:28,35; sin cos tan exp log sqrt tanh atan fabs
+ * pow(T,double) square and + - * / < > work for every T).  The library compiles it at run time
+ * (NVRTC, sm_100a) against its own kernels, instantiating T = double for rollouts and
+ * forward-mode dual numbers (first order for A, B; second order for the cost's gradients and
+ * Hessians) for approximate_model.  A NULL snippet selects a registered model / cost instead,
+ * so user dynamics can be paired with RATILQR_COST_QUADRATIC and vice versa.
+ * After registration, describe problems with  desc.model_id = *model_id_out,
+ * desc.cost_id = RATILQR_COST_USER (cost_src given) or base_cost_id, and the declared n, m,
+ * n_model_params (<= 8), n_cost_params.  Every entry point taking a ratilqr_problem_desc accepts
+ * it (one thread per iLEQG instance; n <= 16, m <= 4).  A NaN/Inf produced by a snippet is that
+ * instance's RATILQR_ST_DOMAIN (Julia: DomainError). */
+#define RATILQR_MODEL_USER_BASE 1000
+#define RATILQR_COST_USER 100
+typedef struct {
+  int32_t n, m;
+  const char* dynamics_src; /* NULL -> registered model base_model_id */
+  int32_t base_model_id;
+  int32_t n_model_params;
+  const char* cost_src;     /* NULL -> registered cost base_cost_id */
+  int32_t base_cost_id;
+  int32_t n_cost_params;    /* user cost: length of cp */
+} ratilqr_user_model_desc;
+/* compile only (NVRTC; no GPU, no ctx): 0 ok, -1 bad description, -20 NVRTC not loadable,
+ * -21 compilation failed.  The compiler log is copied to log (NUL-terminated, truncated). */
+int32_t ratilqr_user_model_check(const ratilqr_user_model_desc* um, char* log, int64_t log_cap);
+/* compile + load into ctx; ids are per ctx and stay valid until ratilqr_destroy */
+int32_t ratilqr_user_model_register(ratilqr_ctx* ctx, const ratilqr_user_model_desc* um,
+                                    int32_t* model_id_out, char* log, int64_t log_cap);
 
 /* ---- measurement utilities --------------------------------------------------------- */
 /* dependent-chain-free DFMA loop on every SM: returns achieved TFLOP/s (FP64, non-tensor) */

@@ -12,7 +12,7 @@ from .ileqg import (ILEQGSolver, NotPositiveDefinite, approximate_model, decreas
                     solve_approximate_dp, solve_approximate_dp_)
 from .models import (CartPole, ConstantCovariance, DeviceStochasticDynamics, DomainError, DoubleIntegrator,  # noqa: F401
                      L1ControlCost, Pendulum, PowerLawCost, PowerLawDynamics, QuadraticCost, Quadrotor,
-                     SingleIntegrator, Unicycle)
+                     SingleIntegrator, Unicycle, UserCost, UserDynamics, register_user_model)
 from .nelder_mead import NelderMeadBilevelOptimizationSolver  # noqa: F401
 from .pets import CrossEntropyDirectOptimizationSolver, PETSSolver  # noqa: F401
 from .problems import (FiniteHorizonGenerativeOptimalControlProblem,  # noqa: F401

@@ -98,6 +98,15 @@ def make_opts(**kw):
                      int(bool(o["f_returns_jacobian"])))
 
 
+class UserModelDesc(C.Structure):  # ratilqr_user_model_desc
+    _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("dynamics_src", C.c_char_p), ("base_model_id", C.c_int32),
+                ("n_model_params", C.c_int32), ("cost_src", C.c_char_p), ("base_cost_id", C.c_int32),
+                ("n_cost_params", C.c_int32)]
+
+
+MODEL_USER_BASE, COST_USER = 1000, 100
+
+
 class Spec:
     """Plain description of a registered problem: what ratilqr_problem_desc carries."""
 
@@ -178,6 +187,35 @@ class CApi:
         self.f_probe_sus = self._fn("fp64_peak_probe_sustained", [vp, f64, dp])
         self.f_launches = self._fn("launch_count", [vp], restype=C.c_int64)
         self.f_pets_solve = self._fn("pets_solve", [vp, PD, GD, dp, i32, i32, i32, i32, f64, dp, dp, C.c_uint64, dp, dp])
+        UM = C.POINTER(UserModelDesc)
+        self.f_um_check = self._fn("user_model_check", [UM, C.c_char_p, C.c_int64])
+        self.f_um_register = self._fn("user_model_register", [vp, UM, ip, C.c_char_p, C.c_int64])
+
+    # -- user-extensible device models (NVRTC) ------------------------------------------------
+    @staticmethod
+    def _um_desc(n, m, dynamics_src, base_model_id, n_model_params, cost_src, base_cost_id, n_cost_params):
+        enc = lambda t: None if t is None else t.encode()
+        return UserModelDesc(int(n), int(m), enc(dynamics_src), int(base_model_id), int(n_model_params), enc(cost_src),
+                             int(base_cost_id), int(n_cost_params))
+
+    def user_model_check(self, n, m, dynamics_src=None, cost_src=None, base_model_id=0, base_cost_id=0,
+                         n_model_params=0, n_cost_params=0):
+        """compile only (no GPU needed) -> (status, compiler log)"""
+        d = self._um_desc(n, m, dynamics_src, base_model_id, n_model_params, cost_src, base_cost_id, n_cost_params)
+        log = C.create_string_buffer(1 << 16)
+        rc = self.f_um_check(C.byref(d), log, len(log))
+        return rc, log.value.decode(errors="replace")
+
+    def user_model_register(self, n, m, dynamics_src=None, cost_src=None, base_model_id=0, base_cost_id=0,
+                            n_model_params=0, n_cost_params=0):
+        """compile + load into this context -> model id to put into Spec.model_id"""
+        d = self._um_desc(n, m, dynamics_src, base_model_id, n_model_params, cost_src, base_cost_id, n_cost_params)
+        log = C.create_string_buffer(1 << 16)
+        mid = C.c_int32(0)
+        rc = self.f_um_register(self.ctx, C.byref(d), C.byref(mid), log, len(log))
+        if rc != 0:
+            raise ApiError(f"user_model_register failed ({rc}): {log.value.decode(errors='replace')[:4000]}")
+        return int(mid.value)
 
     def open(self, device_id=0):
         if self.needs_ctx and not self.ctx:

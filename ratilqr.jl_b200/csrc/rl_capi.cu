@@ -11,6 +11,7 @@
 
 #include "rl_host.hpp"
 #include "rl_launch.hpp"
+#include "rl_user_host.hpp"
 
 namespace {
 
@@ -50,6 +51,9 @@ struct ratilqr_ctx {
   DBuf d_cp, d_W, d_Winv, d_detW, d_x0, d_u, d_theta, d_X, d_U, d_Lg, d_DL;
   DBuf d_value, d_status, d_iters, d_trials, d_restarts, d_mu, d_d, d_cur, d_eps, d_perm;
   DBuf d_out1, d_out2, d_out3;  // host-layout staging for x, l, L
+  // user-extensible device models (NVRTC): id = RATILQR_MODEL_USER_BASE + index
+  std::vector<rlu::Module*> user_models;
+  const rlu::Module* staged_user = nullptr;
   // scratch for component calls
   DBuf s[16];
   DBuf d_cost;
@@ -100,10 +104,48 @@ __global__ void k_ce_cost(int B, const double* value, const int32_t* status, con
   cost[b] = status[b] == 0 ? value[b] + kl / theta[b] : HUGE_VAL;
 }
 
+// ---- user-extensible device models: lookup, validation, launch ------------------------------------------------
+static const rlu::Module* find_user(const ratilqr_ctx* ctx, int model_id) {
+  const int i = model_id - RATILQR_MODEL_USER_BASE;
+  return (i >= 0 && i < (int)ctx->user_models.size()) ? ctx->user_models[i] : nullptr;
+}
+
+// nullptr if the description is fine, else a message; *um receives the user module (or nullptr)
+static const char* check_desc_ctx(const ratilqr_ctx* ctx, const ratilqr_problem_desc* d, bool differentiable,
+                                  const rlu::Module** um) {
+  *um = nullptr;
+  if (!d) return "null problem description";
+  if (d->model_id < RATILQR_MODEL_USER_BASE) return rlh::check_desc(d, differentiable);
+  const rlu::Module* u = find_user(ctx, d->model_id);
+  if (!u) return "unknown user model id (ratilqr_user_model_register returns the id; ids are per ctx)";
+  if (d->n != u->spec.n || d->m != u->spec.m) return "n/m do not match the registered user model";
+  if (d->n_model_params != u->spec.n_model_params || (d->n_model_params > 0 && !d->model_params)) return "wrong number of model parameters";
+  if (d->cost_id != u->cost_id) return "cost_id does not match the registered user model (RATILQR_COST_USER or its base cost)";
+  const int ncp = u->spec.cost_src.empty() ? rlh::cost_param_count(d->cost_id, d->n, d->m) : u->spec.n_cost_params;
+  if (d->n_cost_params != ncp || (ncp > 0 && !d->cost_params)) return "wrong number of cost parameters";
+  if (d->N < 1) return "N must be >= 1";
+  if (d->cost_params_count < 1) return "cost_params_count must be >= 1";
+  if (differentiable && !u->differentiable) return "L1_CONTROL cost is rollout-only (PETS)";
+  if (!d->W) return "W is null";
+  *um = u;
+  return nullptr;
+}
+
+static int user_launch(ratilqr_ctx* ctx, const rlu::Module* um, rlu::Kernel k, unsigned gx, unsigned gy, unsigned block,
+                       size_t smem, void* args, const char* what) {
+  std::string e;
+  if (int rc = rlu::launch(*um, k, gx, gy, block, smem, ctx->stream, args, e)) { ctx->err = std::string(what) + " (user model): " + e; return rc; }
+  ctx->launches += 1;
+  return 0;
+}
+#define RL_GRID(total, th) ((unsigned)(((total) + (th)-1) / (th)))
+
 static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
                           const ratilqr_batch_in* in, int eps_cap, bool device_theta = false, int want_traj = 0) {
   ctx->staged = false;
-  if (const char* m = rlh::check_desc(desc, true)) FAIL(-1, m);
+  const rlu::Module* um = nullptr;
+  if (const char* m = check_desc_ctx(ctx, desc, true, &um)) FAIL(-1, m);
+  ctx->staged_user = um;
   if (const char* m = check_opts(opts)) FAIL(-3, m);
   if (!in || in->P < 1 || in->K < 1 || !in->x0 || !in->u_init || (!in->theta && !device_theta)) FAIL(-1, "bad batch description");
   if ((in->x0_count != 1 && in->x0_count != in->P) || (in->u_count != 1 && in->u_count != in->P)) FAIL(-1, "x0_count/u_count must be 1 or P");
@@ -168,7 +210,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   }
   ctx->model_id = desc->model_id;
   // structure-specialised kernel when the quadratic cost is diagonal (bit-identical results, fewer flops)
-  ctx->cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
+  ctx->cost_id = (!um && rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
   ctx->n = n; ctx->m = m; ctx->N = N; ctx->B = (int)B; ctx->eps_cap = eps_cap;
   // kernel choice: the warp-cooperative kernel when the per-stage state is too big for one thread's registers
   // (n > 6: the quadrotor); one thread per instance otherwise.  (For n = 4 the ~20 synchronised shared-memory
@@ -177,7 +219,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   ctx->coop_cost_id = rlh::quad_is_diag(desc) ? RL_COST_QUAD_DIAG : desc->cost_id;
   if (desc->model_id == RATILQR_MODEL_POWER_LAW) ctx->coop_cost_id = desc->cost_id;
   size_t csm = 0;
-  if (rll::coop_smem_query(desc->model_id, ctx->coop_cost_id, N, &csm) == 0) {
+  if (!um && rll::coop_smem_query(desc->model_id, ctx->coop_cost_id, N, &csm) == 0) {  // user models: one thread per instance
     size_t per_sm = (227 * 1024) / (csm + 1024);
     if (per_sm > 32) per_sm = 32;
     int sms = 148;
@@ -231,6 +273,11 @@ static int run_internal(ratilqr_ctx* ctx, int reps, float* ms_total) {
       continue;
     }
     if (ctx->dynamic) CU(cudaMemsetAsync(ctx->sp.queue, 0, 4, ctx->stream));
+    if (ctx->staged_user) {
+      const rlu::Module* um = ctx->staged_user;
+      if (int rc = user_launch(ctx, um, rlu::K_SOLVE, RL_GRID(ctx->sp.B, 64), 1, 64, um->solve_smem, &ctx->sp, "k_ileqg_solve")) return rc;
+      continue;
+    }
     if (rll::launch_solve(ctx->model_id, ctx->cost_id, ctx->sp, ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
     if (int rc = check_launch(ctx, "k_ileqg_solve")) return rc;
   }
@@ -348,10 +395,65 @@ int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
                  &ctx->d_out3, &ctx->d_cost, &ctx->d_coop_traj, &ctx->d_queue};
   for (DBuf* b : all) b->release();
   for (DBuf& b : ctx->s) b.release();
+  for (rlu::Module* um : ctx->user_models) { rlu::unload(*um); delete um; }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return 0;
+}
+
+static void copy_log(const std::string& src, char* log, int64_t cap) {
+  if (!log || cap < 1) return;
+  size_t k = src.size() < (size_t)cap - 1 ? src.size() : (size_t)cap - 1;
+  memcpy(log, src.data(), k);
+  log[k] = 0;
+}
+
+static int user_spec_from(const ratilqr_user_model_desc* um, rlu::Spec& sp) {
+  if (!um) return -1;
+  sp.n = um->n; sp.m = um->m; sp.n_model_params = um->n_model_params; sp.n_cost_params = um->n_cost_params;
+  sp.base_model_id = um->base_model_id; sp.base_cost_id = um->base_cost_id;
+  sp.dynamics_src = um->dynamics_src ? um->dynamics_src : "";
+  sp.cost_src = um->cost_src ? um->cost_src : "";
+  if (sp.dynamics_src.empty()) {  // registered dynamics: its own parameter count
+    int n, m, np;
+    if (rlh::model_dims(sp.base_model_id, &n, &m, &np)) sp.n_model_params = np;
+  }
+  if (sp.cost_src.empty()) sp.n_cost_params = rlh::cost_param_count(sp.base_cost_id, sp.n, sp.m);
+  return 0;
+}
+
+int32_t ratilqr_user_model_check(const ratilqr_user_model_desc* um, char* log, int64_t log_cap) {
+  rlu::Spec sp;
+  if (user_spec_from(um, sp)) return -1;
+  rlu::Compiled c;
+  int rc = rlu::compile(sp, c);
+  copy_log(c.log, log, log_cap);
+  return rc;
+}
+
+int32_t ratilqr_user_model_register(ratilqr_ctx* ctx, const ratilqr_user_model_desc* um, int32_t* model_id_out, char* log,
+                                    int64_t log_cap) {
+  if (!ctx) return -1;
+  if (!model_id_out) FAIL(-1, "model_id_out is null");
+  rlu::Spec sp;
+  if (user_spec_from(um, sp)) FAIL(-1, "null user model description");
+  rlu::Compiled c;
+  int rc = rlu::compile(sp, c);
+  copy_log(c.log, log, log_cap);
+  if (rc) FAIL(rc, "user model: " + (c.log.empty() ? std::string("compilation failed") : c.log));
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaFree(0));  // make sure the primary context is current before the driver-API load
+  rlu::Module* mod = new rlu::Module();
+  mod->spec = sp;
+  mod->id = RATILQR_MODEL_USER_BASE + (int)ctx->user_models.size();
+  mod->cost_id = sp.cost_src.empty() ? sp.base_cost_id : RATILQR_COST_USER;
+  mod->differentiable = !sp.cost_src.empty() || sp.base_cost_id != RATILQR_COST_L1_CONTROL;
+  std::string e;
+  if ((rc = rlu::load(c, *mod, e))) { delete mod; FAIL(rc, "user model: " + e); }
+  ctx->user_models.push_back(mod);
+  *model_id_out = mod->id;
   return 0;
 }
 
@@ -411,9 +513,10 @@ int32_t ratilqr_ce_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, con
 }
 
 // ---- component entry points ---------------------------------------------------------------------
-static int fill_comp(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int B, rll::CompArgs& a, bool differentiable) {
+static int fill_comp(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int B, rll::CompArgs& a, bool differentiable,
+                     const rlu::Module** um) {
   ctx->staged = false;  // shares d_cp / d_W with a staged solve
-  if (const char* m = rlh::check_desc(desc, differentiable)) FAIL(-1, m);
+  if (const char* m = check_desc_ctx(ctx, desc, differentiable, um)) FAIL(-1, m);
   if (B < 1) FAIL(-1, "B must be >= 1");
   CU(cudaSetDevice(ctx->device));
   memset(&a, 0, sizeof(a));
@@ -430,14 +533,16 @@ int32_t ratilqr_rollout_open_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc*
                                    const double* u, double* x, int32_t* status) {
   if (!ctx) return -1;
   rll::CompArgs a;
-  if (int rc = fill_comp(ctx, desc, B, a, false)) return rc;
+  const rlu::Module* um = nullptr;
+  if (int rc = fill_comp(ctx, desc, B, a, false, &um)) return rc;
   const size_t n = a.n, m = a.m, N = a.N;
   UP(ctx->s[0], x0, n * B * 8); UP(ctx->s[1], u, m * N * B * 8);
   CU(ctx->s[2].reserve(n * (N + 1) * B * 8)); CU(ctx->s[3].reserve((size_t)B * 4));
   CU(cudaMemsetAsync(ctx->s[2].p, 0, n * (N + 1) * B * 8, ctx->stream));
   a.x0 = ctx->s[0].as<double>(); a.u = ctx->s[1].as<double>(); a.x = ctx->s[2].as<double>(); a.status = ctx->s[3].as<int32_t>();
-  if (rll::launch_rollout_open(a, ctx->stream)) FAIL(-5, "model not compiled in");
-  if (int rc = check_launch(ctx, "k_rollout_open")) return rc;
+  if (um) { if (int rc = user_launch(ctx, um, rlu::K_ROLLOUT_OPEN, RL_GRID(a.B, 64), 1, 64, 0, &a, "k_rollout_open")) return rc; }
+  else if (rll::launch_rollout_open(a, ctx->stream)) FAIL(-5, "model not compiled in");
+  if (int rc = check_launch(ctx, "k_rollout_open", um ? 0 : 1)) return rc;
   DOWNSYNC(x, a.x, n * (N + 1) * B * 8); DOWNSYNC(status, a.status, (size_t)B * 4);
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -447,14 +552,16 @@ int32_t ratilqr_rollout_closed_batch(ratilqr_ctx* ctx, const ratilqr_problem_des
                                      const double* l, const double* L, double* x_new, double* u_new, int32_t* status) {
   if (!ctx) return -1;
   rll::CompArgs a;
-  if (int rc = fill_comp(ctx, desc, B, a, false)) return rc;
+  const rlu::Module* um = nullptr;
+  if (int rc = fill_comp(ctx, desc, B, a, false, &um)) return rc;
   const size_t n = a.n, m = a.m, N = a.N;
   UP(ctx->s[0], xbar, n * (N + 1) * B * 8); UP(ctx->s[1], l, m * N * B * 8); UP(ctx->s[2], L, m * n * N * B * 8);
   CU(ctx->s[3].reserve(n * (N + 1) * B * 8)); CU(ctx->s[4].reserve(m * N * B * 8)); CU(ctx->s[5].reserve((size_t)B * 4));
   a.xbar = ctx->s[0].as<double>(); a.l = ctx->s[1].as<double>(); a.L = ctx->s[2].as<double>();
   a.x = ctx->s[3].as<double>(); a.u_new = ctx->s[4].as<double>(); a.status = ctx->s[5].as<int32_t>();
-  if (rll::launch_rollout_closed(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
-  if (int rc = check_launch(ctx, "k_rollout_closed")) return rc;
+  if (um) { if (int rc = user_launch(ctx, um, rlu::K_ROLLOUT_CLOSED, RL_GRID(a.B, 64), 1, 64, 0, &a, "k_rollout_closed")) return rc; }
+  else if (rll::launch_rollout_closed(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  if (int rc = check_launch(ctx, "k_rollout_closed", um ? 0 : 1)) return rc;
   DOWNSYNC(x_new, a.x, n * (N + 1) * B * 8); DOWNSYNC(u_new, a.u_new, m * N * B * 8); DOWNSYNC(status, a.status, (size_t)B * 4);
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -464,13 +571,15 @@ int32_t ratilqr_integrate_cost_batch(ratilqr_ctx* ctx, const ratilqr_problem_des
                                      const double* u, double* cost, int32_t* status) {
   if (!ctx) return -1;
   rll::CompArgs a;
-  if (int rc = fill_comp(ctx, desc, B, a, false)) return rc;
+  const rlu::Module* um = nullptr;
+  if (int rc = fill_comp(ctx, desc, B, a, false, &um)) return rc;
   const size_t n = a.n, m = a.m, N = a.N;
   UP(ctx->s[0], x, n * (N + 1) * B * 8); UP(ctx->s[1], u, m * N * B * 8);
   CU(ctx->s[2].reserve((size_t)B * 8)); CU(ctx->s[3].reserve((size_t)B * 4));
   a.x = ctx->s[0].as<double>(); a.u = ctx->s[1].as<double>(); a.cost = ctx->s[2].as<double>(); a.status = ctx->s[3].as<int32_t>();
-  if (rll::launch_integrate_cost(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
-  if (int rc = check_launch(ctx, "k_integrate_cost")) return rc;
+  if (um) { if (int rc = user_launch(ctx, um, rlu::K_INTEGRATE_COST, RL_GRID(a.B, 64), 1, 64, 0, &a, "k_integrate_cost")) return rc; }
+  else if (rll::launch_integrate_cost(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  if (int rc = check_launch(ctx, "k_integrate_cost", um ? 0 : 1)) return rc;
   DOWNSYNC(cost, a.cost, (size_t)B * 8); DOWNSYNC(status, a.status, (size_t)B * 4);
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -481,7 +590,8 @@ int32_t ratilqr_linearize_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
                                 double* A, double* Bm, int32_t* status) {
   if (!ctx) return -1;
   rll::CompArgs a;
-  if (int rc = fill_comp(ctx, desc, B, a, true)) return rc;
+  const rlu::Module* um = nullptr;
+  if (int rc = fill_comp(ctx, desc, B, a, true, &um)) return rc;
   const size_t n = a.n, m = a.m, N = a.N;
   const size_t sz[8] = {(N + 1) * B, n * (N + 1) * B, n * n * (N + 1) * B, m * N * B, m * m * N * B, m * n * N * B, n * n * N * B, n * m * N * B};
   UP(ctx->s[0], x, n * (N + 1) * B * 8); UP(ctx->s[1], u, m * N * B * 8);
@@ -492,8 +602,9 @@ int32_t ratilqr_linearize_batch(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
   a.q = ctx->s[2].as<double>(); a.qv = ctx->s[3].as<double>(); a.Q = ctx->s[4].as<double>(); a.r = ctx->s[5].as<double>();
   a.R = ctx->s[6].as<double>(); a.Pm = ctx->s[7].as<double>(); a.A = ctx->s[8].as<double>(); a.Bm = ctx->s[9].as<double>();
   a.status = ctx->s[10].as<int32_t>();
-  if (rll::launch_linearize(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
-  if (int rc = check_launch(ctx, "k_linearize")) return rc;
+  if (um) { if (int rc = user_launch(ctx, um, rlu::K_LINEARIZE, RL_GRID((size_t)a.B * (a.N + 1), 64), 1, 64, 0, &a, "k_linearize")) return rc; }
+  else if (rll::launch_linearize(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  if (int rc = check_launch(ctx, "k_linearize", um ? 0 : 1)) return rc;
   double* outs[8] = {q, qv, Q, r, R, Pm, A, Bm};
   for (int i = 0; i < 8; ++i) DOWNSYNC(outs[i], ctx->s[2 + i].p, sz[i] * 8);
   DOWNSYNC(status, a.status, (size_t)B * 4);
@@ -549,7 +660,8 @@ int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, i
                            const double* l, const double* L, int32_t n_samples, const double* noise, uint64_t seed,
                            double theta_risk, double* J, double* stats, double* x_out) {
   if (!ctx) return -1;
-  if (const char* msg = rlh::check_desc(desc, false)) FAIL(-1, msg);
+  const rlu::Module* um = nullptr;
+  if (const char* msg = check_desc_ctx(ctx, desc, false, &um)) FAIL(-1, msg);
   if (P < 1 || n_samples < 1 || !xbar || !l || !L) FAIL(-1, "bad arguments");
   if (desc->cost_params_count != 1 && desc->cost_params_count != P) FAIL(-1, "cost_params_count must be 1 or P");
   ctx->staged = false;
@@ -570,8 +682,9 @@ int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, i
   a.cholW = ctx->s[4].as<double>(); a.W_tv = desc->W_time_varying; a.seed = seed;
   CU(ctx->s[5].reserve(S * 8)); a.J = ctx->s[5].as<double>();
   if (x_out) { CU(ctx->s[6].reserve(n * (N + 1) * S * 8)); a.x_out = ctx->s[6].as<double>(); }
-  if (rll::launch_mc_rollout(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
-  if (int rc = check_launch(ctx, "k_mc_rollout")) return rc;
+  if (um) { if (int rc = user_launch(ctx, um, rlu::K_MC_ROLLOUT, RL_GRID(a.n_samples, 128), (unsigned)a.P, 128, 0, &a, "k_mc_rollout")) return rc; }
+  else if (rll::launch_mc_rollout(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  if (int rc = check_launch(ctx, "k_mc_rollout", um ? 0 : 1)) return rc;
   if (stats) {
     CU(ctx->s[7].reserve((size_t)P * 24));
     rll::launch_mc_stats(a.J, n_samples, P, theta_risk, ctx->s[7].as<double>(), ctx->stream);
@@ -584,9 +697,18 @@ int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, i
   return 0;
 }
 
+static int pets_launch_costs(ratilqr_ctx* ctx, const rlu::Module* um, rll::PetsArgs& a) {
+  if (um) {
+    const unsigned th = a.particles >= 256 ? 256 : ((a.particles + 31) / 32) * 32;
+    return user_launch(ctx, um, rlu::K_PETS_COSTS, (unsigned)a.C, 1, th, 0, &a, "k_pets_costs");
+  }
+  if (rll::launch_pets_costs(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+  return 0;
+}
+
 static int pets_fill(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_generative_desc* gen,
-                     const double* x0, int C, int particles, rll::PetsArgs& a) {
-  if (const char* msg = rlh::check_desc(desc, false)) FAIL(-1, msg);
+                     const double* x0, int C, int particles, rll::PetsArgs& a, const rlu::Module** um) {
+  if (const char* msg = check_desc_ctx(ctx, desc, false, um)) FAIL(-1, msg);
   if (C < 1 || particles < 1 || !x0) FAIL(-1, "bad arguments");
   ctx->staged = false;
   CU(cudaSetDevice(ctx->device));
@@ -618,7 +740,8 @@ int32_t ratilqr_pets_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, c
   if (!ctx) return -1;
   if (!controls || !cost) FAIL(-1, "null argument");
   rll::PetsArgs a;
-  if (int rc = pets_fill(ctx, desc, gen, x0, C, particles, a)) return rc;
+  const rlu::Module* um = nullptr;
+  if (int rc = pets_fill(ctx, desc, gen, x0, C, particles, a, &um)) return rc;
   const size_t n = desc->n, m = desc->m, N = desc->N;
   UP(ctx->s[0], controls, m * N * C * 8);
   a.controls = ctx->s[0].as<double>();
@@ -626,8 +749,8 @@ int32_t ratilqr_pets_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, c
   a.seed = seed; a.stream_offset = 0;
   CU(ctx->s[2].reserve((size_t)C * 8));
   a.cost = ctx->s[2].as<double>();
-  if (rll::launch_pets_costs(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
-  if (int rc = check_launch(ctx, "k_pets_costs")) return rc;
+  if (int rc = pets_launch_costs(ctx, um, a)) return rc;
+  if (int rc = check_launch(ctx, "k_pets_costs", um ? 0 : 1)) return rc;
   DOWNSYNC(cost, a.cost, (size_t)C * 8);
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -658,7 +781,8 @@ int32_t ratilqr_pets_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, c
   if (!ctx) return -1;
   if (!mu || !Sigma || num_elite < 2 || num_elite > C || iter_max < 0) FAIL(-1, "bad arguments");
   rll::PetsArgs a;
-  if (int rc = pets_fill(ctx, desc, gen, x0, C, particles, a)) return rc;
+  const rlu::Module* um = nullptr;
+  if (int rc = pets_fill(ctx, desc, gen, x0, C, particles, a, &um)) return rc;
   const size_t n = desc->n, m = desc->m, N = desc->N;
   const size_t zsz = m * N * C, nsz = n * N * (size_t)particles * C;
   if (z_inject) UP(ctx->s[1], z_inject, zsz * iter_max * 8);
@@ -674,10 +798,10 @@ int32_t ratilqr_pets_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, c
                             (uint64_t)it * (uint64_t)C, ctx->s[0].as<double>(), ctx->s[6].as<int32_t>(), ctx->stream);
     a.noise = noise ? ctx->s[11].as<double>() + nsz * it : nullptr;
     a.stream_offset = (uint64_t)it * (uint64_t)C * (uint64_t)particles;
-    if (rll::launch_pets_costs(a, ctx->stream)) FAIL(-5, "(model, cost) pair not compiled in");
+    if (int rc = pets_launch_costs(ctx, um, a)) return rc;
     rll::launch_pets_refit(desc->m, desc->N, C, num_elite, smoothing, a.controls, a.cost, ctx->s[3].as<double>(),
                            ctx->s[4].as<double>(), ctx->s[5].as<int32_t>(), nullptr, ctx->stream);
-    if (int rc = check_launch(ctx, "pets step", 4)) return rc;
+    if (int rc = check_launch(ctx, "pets step", um ? 3 : 4)) return rc;
   }
   int32_t err = 0;
   CU(cudaMemcpyAsync(&err, ctx->s[6].p, 4, cudaMemcpyDeviceToHost, ctx->stream));

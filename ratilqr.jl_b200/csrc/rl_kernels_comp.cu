@@ -1,5 +1,5 @@
 // rl_kernels_comp.cu -- component kernels (unit-parity API), Monte Carlo rollouts and PETS.
-#include "rl_components.cuh"
+#include "rl_kernels_model.cuh"
 #include "rl_host.hpp"
 #include "rl_launch.hpp"
 
@@ -7,70 +7,18 @@ namespace rll {
 
 using namespace rl;
 
-struct Mp8 { double v[8]; };
-static Mp8 mk_mp(const double* mp) { Mp8 r; for (int i = 0; i < 8; ++i) r.v[i] = mp[i]; return r; }
-
-// ---- rollouts / cost / linearize: thread = instance (host layout, instance slowest) ----------
-template <class D>
-__global__ void k_rollout_open(Mp8 mp, int N, int B, const double* x0, const double* u, double* x, int32_t* status) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  constexpr int n = D::n, m = D::m;
-  int st = comp_rollout_open<D>(mp.v, N, x0 + (size_t)b * n, u + (size_t)b * m * N, x + (size_t)b * n * (N + 1));
-  if (status) status[b] = st;
-}
-
-template <class D, class CT>
-__global__ void k_rollout_closed(Mp8 mp, const double* cp, int N, int B, const double* xbar, const double* l,
-                                 const double* L, double* xn, double* un, int32_t* status) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  constexpr int n = D::n, m = D::m;
-  int st = comp_rollout_closed<D, CT>(mp.v, cp, N, xbar + (size_t)b * n * (N + 1), l + (size_t)b * m * N,
-                                      L + (size_t)b * m * n * N, nullptr, xn + (size_t)b * n * (N + 1),
-                                      un + (size_t)b * m * N, nullptr);
-  if (status) status[b] = st;
-}
-
-template <class D, class CT>
-__global__ void k_integrate_cost(const double* cp, int N, int B, const double* x, const double* u, double* cost,
-                                 int32_t* status) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  constexpr int n = D::n, m = D::m;
-  double c = HUGE_VAL;
-  int st = comp_integrate_cost<D, CT>(cp, N, x + (size_t)b * n * (N + 1), u + (size_t)b * m * N, &c);
-  cost[b] = st ? HUGE_VAL : c;
-  if (status) status[b] = st;
-}
-
-// approximate_model is embarrassingly parallel over stages (ileqg.jl:293): thread = (stage, instance)
-template <class D, class CT>
-__global__ void k_linearize(Mp8 mp, const double* cp, int N, int B, const double* x, const double* u, double* q,
-                            double* qv, double* Q, double* r, double* R, double* Pm, double* A, double* Bm,
-                            int32_t* status) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= B * (N + 1)) return;
-  constexpr int n = D::n, m = D::m;
-  int b = t / (N + 1), k = t % (N + 1);
-  int st = comp_linearize_stage<D, CT>(mp.v, cp, N, k, x + (size_t)b * n * (N + 1), u + (size_t)b * m * N,
-                                       q + (size_t)b * (N + 1), qv + (size_t)b * n * (N + 1),
-                                       Q + (size_t)b * n * n * (N + 1), r + (size_t)b * m * N, R + (size_t)b * m * m * N,
-                                       Pm + (size_t)b * m * n * N, A + (size_t)b * n * n * N, Bm + (size_t)b * n * m * N);
-  if (st && status) atomicMax(&status[b], st);
-}
 
 #define RL_BLOCKS(total, th) (((total) + (th)-1) / (th))
 
 int launch_rollout_open(const CompArgs& a, cudaStream_t st) {
-#define X(MID, CID) if (a.model_id == MID) { k_rollout_open<Dyn<MID>><<<RL_BLOCKS(a.B, 64), 64, 0, st>>>(mk_mp(a.mp), a.N, a.B, a.x0, a.u, a.x, a.status); return 0; }
+#define X(MID, CID) if (a.model_id == MID) { k_rollout_open<Dyn<MID>><<<RL_BLOCKS(a.B, 64), 64, 0, st>>>(a); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)
 #undef X
   return -1;
 }
 
 int launch_rollout_closed(const CompArgs& a, cudaStream_t st) {
-#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_rollout_closed<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<RL_BLOCKS(a.B, 64), 64, 0, st>>>(mk_mp(a.mp), a.cp, a.N, a.B, a.xbar, a.l, a.L, a.x, a.u_new, a.status); return 0; }
+#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_rollout_closed<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<RL_BLOCKS(a.B, 64), 64, 0, st>>>(a); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)
   RL_FOR_EACH_ROLLOUT_ONLY_COMBO(X)
 #undef X
@@ -78,7 +26,7 @@ int launch_rollout_closed(const CompArgs& a, cudaStream_t st) {
 }
 
 int launch_integrate_cost(const CompArgs& a, cudaStream_t st) {
-#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_integrate_cost<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<RL_BLOCKS(a.B, 64), 64, 0, st>>>(a.cp, a.N, a.B, a.x, a.u, a.cost, a.status); return 0; }
+#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_integrate_cost<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<RL_BLOCKS(a.B, 64), 64, 0, st>>>(a); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)
   RL_FOR_EACH_ROLLOUT_ONLY_COMBO(X)
 #undef X
@@ -86,7 +34,7 @@ int launch_integrate_cost(const CompArgs& a, cudaStream_t st) {
 }
 
 int launch_linearize(const CompArgs& a, cudaStream_t st) {
-#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_linearize<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<RL_BLOCKS(a.B * (a.N + 1), 64), 64, 0, st>>>(mk_mp(a.mp), a.cp, a.N, a.B, a.x, a.u, a.q, a.qv, a.Q, a.r, a.R, a.Pm, a.A, a.Bm, a.status); return 0; }
+#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_linearize<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<RL_BLOCKS(a.B * (a.N + 1), 64), 64, 0, st>>>(a); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)
 #undef X
   return -1;
@@ -120,86 +68,14 @@ int launch_riccati(const RiccatiArgs& a, cudaStream_t st) {
   return -1;
 }
 
-// ---- Monte Carlo closed-loop rollouts (ileqg.jl:94-109 + :115-124): thread = sample -------------
-// The policy (xbar, l, L) of a problem is read by every thread of the block through the
-// read-only path (same address across the warp => one broadcast transaction); the injected
-// noise row of a sample is a contiguous n*N block (each 32-byte sector fully used).
-template <class D, class CT>
-__global__ void __launch_bounds__(128) k_mc_rollout(McArgs a, Mp8 mp) {
-  constexpr int n = D::n, m = D::m;
-  int p = blockIdx.y;
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= a.n_samples) return;
-  size_t gi = (size_t)p * a.n_samples + s;
-  int N = a.N;
-  const double* cp = a.cp + (a.cp_count > 1 ? (size_t)p * a.ncp : 0);
-  const double* xbar = a.xbar + (size_t)p * n * (N + 1);
-  const double* l = a.l + (size_t)p * m * N;
-  const double* L = a.L + (size_t)p * m * n * N;
-  double cost = HUGE_VAL;
-  int st;
-  if (a.noise) {
-    st = comp_rollout_closed<D, CT>(mp.v, cp, N, xbar, l, L, a.noise + gi * n * N,
-                                    a.x_out ? a.x_out + gi * n * (N + 1) : nullptr, nullptr, &cost);
-  } else {
-    // Philox mode: same loop with generated noise
-    double x[n], xn[n], u[m], w[n];
-    for (int i = 0; i < n; ++i) { x[i] = xbar[i]; if (a.x_out) a.x_out[gi * n * (N + 1) + i] = x[i]; }
-    double J = 0.0;
-    st = 0;
-    for (int k = 0; k < N && !st; ++k) {
-      double dx[n];
-      for (int i = 0; i < n; ++i) dx[i] = x[i] - xbar[(size_t)k * n + i];
-      const double* Lk = L + (size_t)k * m * n;
-      for (int j = 0; j < m; ++j) {
-        double acc = Lk[j] * dx[0];
-        for (int i = 1; i < n; ++i) acc = rl_fma(Lk[j + i * m], dx[i], acc);
-        u[j] = l[(size_t)k * m + j] + acc;
-      }
-      double q;
-      if (!CT::stage(cp, k, x, u, false, q, nullptr, nullptr, nullptr, nullptr, nullptr)) { st = RATILQR_ST_DOMAIN; break; }
-      J += q;
-      if (!D::f(mp.v, x, u, xn)) { st = RATILQR_ST_DOMAIN; break; }
-      philox_noise<n>(a.seed, gi, (uint32_t)k, 0, 1.0, a.cholW + (a.W_tv ? (size_t)k * n * n : 0), w);
-      for (int i = 0; i < n; ++i) { x[i] = xn[i] + w[i]; if (a.x_out) a.x_out[gi * n * (N + 1) + (size_t)(k + 1) * n + i] = x[i]; }
-    }
-    if (!st) {
-      double q;
-      if (!CT::terminal(cp, x, false, q, nullptr, nullptr)) st = RATILQR_ST_DOMAIN; else cost = J + q;
-    }
-  }
-  a.J[gi] = st ? HUGE_VAL : cost;
-}
-
 int launch_mc_rollout(const McArgs& a, cudaStream_t st) {
   dim3 grid(RL_BLOCKS(a.n_samples, 128), a.P);
-#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_mc_rollout<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<grid, 128, 0, st>>>(a, mk_mp(a.mp)); return 0; }
+#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_mc_rollout<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<grid, 128, 0, st>>>(a); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)
   RL_FOR_EACH_ROLLOUT_ONLY_COMBO(X)
 #undef X
   return -1;
 }
-
-// fixed-shape block reductions (deterministic): one block per problem
-template <class Op>
-__device__ double block_reduce(double v, Op op, double neutral, double* sh) {
-  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_down_sync(0xffffffffu, v, o));
-  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  int nw = (blockDim.x + 31) >> 5;
-  if (w == 0) {
-    double acc = (lane < nw) ? sh[lane] : neutral;
-    for (int o = 16; o > 0; o >>= 1) acc = op(acc, __shfl_down_sync(0xffffffffu, acc, o));
-    if (lane == 0) sh[32] = acc;
-  }
-  __syncthreads();
-  double r = sh[32];
-  __syncthreads();
-  return r;
-}
-struct OpAdd { __device__ double operator()(double a, double b) const { return a + b; } };
-struct OpMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
 
 __global__ void __launch_bounds__(256) k_mc_stats(const double* J, int n_samples, double theta_risk, double* stats) {
   __shared__ double sh[33];
@@ -229,30 +105,9 @@ void launch_mc_stats(const double* J, int n_samples, int P, double theta_risk, d
   k_mc_stats<<<P, 256, 0, st>>>(J, n_samples, theta_risk, stats);
 }
 
-// ---- PETS: compute_cost_serial (pets.jl:128-157): block = sequence, thread = particle -------------
-template <class D, class CT>
-__global__ void __launch_bounds__(256) k_pets_costs(PetsArgs a, Mp8 mp) {
-  constexpr int n = D::n, m = D::m;
-  __shared__ double sh[33];
-  int ii = blockIdx.x;
-  double acc = 0.0;
-  int per = a.n_ens > 1 ? max(a.particles / a.n_ens, 1) : a.particles;
-  for (int kk = threadIdx.x; kk < a.particles; kk += blockDim.x) {
-    const double* mpp = mp.v;
-    if (a.ens_params && a.n_ens > 1) mpp = a.ens_params + (size_t)min(kk / per, a.n_ens - 1) * a.n_mp;
-    size_t gi = (size_t)ii * a.particles + kk;
-    double c = comp_pets_particle<D, CT>(mpp, a.cp, a.N, a.x0, a.controls + (size_t)ii * m * a.N,
-                                         a.noise ? a.noise + gi * n * a.N : nullptr, a.seed, a.stream_offset + gi,
-                                         a.noise_kind, a.noise_scale, a.cholW);
-    acc += c;
-  }
-  double tot = block_reduce(acc, OpAdd(), 0.0, sh);
-  if (threadIdx.x == 0) a.cost[ii] = tot / a.particles;  // mean over particles (pets.jl:154)
-}
-
 int launch_pets_costs(const PetsArgs& a, cudaStream_t st) {
   int th = a.particles >= 256 ? 256 : ((a.particles + 31) / 32) * 32;
-#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_pets_costs<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<a.C, th, 0, st>>>(a, mk_mp(a.mp)); return 0; }
+#define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_pets_costs<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<a.C, th, 0, st>>>(a); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)
   RL_FOR_EACH_ROLLOUT_ONLY_COMBO(X)
 #undef X

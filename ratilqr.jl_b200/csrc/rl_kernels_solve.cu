@@ -11,23 +11,13 @@
 #include <cstring>
 
 #include "rl_coop.cuh"
+#include "rl_kernels_model.cuh"
 #include "rl_host.hpp"
 #include "rl_launch.hpp"
 
 namespace rll {
 
 using namespace rl;
-
-template <class D, class CT, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_ileqg_solve(const __grid_constant__ SolveParams P) {
-  extern __shared__ double stage_area[];  // [2][RL_STAGE_NV][THREADS] doubles when staging is enabled, else empty
-  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  Stage sg;
-  sg.base = (UseStage<D>::value && P.use_stage) ? stage_area + threadIdx.x : nullptr;
-  sg.stride = THREADS;
-  if (P.queue) solve_dynamic<D, CT>(P, b, sg);  // persistent: every thread keeps pulling instances
-  else if (b < (size_t)P.B) solve_instance<D, CT>(P, b, sg);
-}
 
 template <class D, class CT, int THREADS, int MINB>
 static void launch_shape(const SolveParams& P, cudaStream_t st) {

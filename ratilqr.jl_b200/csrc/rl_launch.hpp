@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "rl_args.hpp"
 #include "rl_core.cuh"
 
 namespace rll {
@@ -23,16 +24,6 @@ void launch_gather(int n, int m, int N, int B, const double* X, const double* U,
 // per-problem ascending sort of theta -> slot-to-instance permutation; returns -1 when not applicable
 int launch_sort_theta(const double* theta, int P, int K, int32_t* perm, cudaStream_t st);
 
-struct CompArgs {
-  int model_id, cost_id, n, m, N, B;
-  double mp[8];
-  const double* cp;  // device, one block
-  // rollouts / cost / linearize (host layout, instance slowest)
-  const double *x0, *u, *xbar, *l, *L;
-  double *x, *u_new, *cost;
-  double *q, *qv, *Q, *r, *R, *Pm, *A, *Bm;
-  int32_t* status;
-};
 int launch_rollout_open(const CompArgs& a, cudaStream_t st);
 int launch_rollout_closed(const CompArgs& a, cudaStream_t st);
 int launch_integrate_cost(const CompArgs& a, cudaStream_t st);
@@ -50,33 +41,10 @@ struct RiccatiArgs {
 };
 int launch_riccati(const RiccatiArgs& a, cudaStream_t st);
 
-struct McArgs {
-  int model_id, cost_id, N, P, n_samples;
-  double mp[8];
-  const double* cp; int ncp, cp_count;
-  const double *xbar, *l, *L;        // per problem
-  const double* noise;               // n*N*n_samples*P or null
-  const double* cholW; int W_tv;     // n*n [*N]
-  uint64_t seed;
-  double* J; double* x_out;
-};
 int launch_mc_rollout(const McArgs& a, cudaStream_t st);
 // per-problem mean / unbiased variance / entropic risk of J (deterministic single-block reduction)
 void launch_mc_stats(const double* J, int n_samples, int P, double theta_risk, double* stats, cudaStream_t st);
 
-struct PetsArgs {
-  int model_id, cost_id, N, C, particles;
-  double mp[8];
-  const double* ens_params; int n_ens, n_mp;  // device, or null
-  const double* cp;
-  const double* x0;
-  const double* controls;  // m*N*C
-  const double* noise;     // n*N*particles*C or null
-  const double* cholW;
-  int noise_kind; double noise_scale;
-  uint64_t seed; uint64_t stream_offset;
-  double* cost;            // C
-};
 int launch_pets_costs(const PetsArgs& a, cudaStream_t st);
 // u = mu_t + chol_lower(Sigma_t) z ; z injected (m*N*C) or Philox. returns via err[0] != 0 if a Sigma_t is not PD
 void launch_pets_sample(int m, int N, int C, const double* mu, const double* Sigma, const double* z, uint64_t seed,

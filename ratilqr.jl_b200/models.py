@@ -124,9 +124,10 @@ class DeviceDynamics:
         assert self.params.size == npar, f"model {model_id} takes {npar} parameters"
 
     def __call__(self, x, u, f_returns_jacobian=False):
-        xn = dynamics_numpy(self.model_id, self.params, np.asarray(x, float), np.asarray(u, float))
+        mid = getattr(self, "host_model_id", self.model_id)  # (a registered model bound to a user cost keeps its own id here)
+        xn = dynamics_numpy(mid, self.params, np.asarray(x, float), np.asarray(u, float))
         if f_returns_jacobian:
-            A, B = jacobians_complex_step(self.model_id, self.params, x, u)
+            A, B = jacobians_complex_step(mid, self.params, x, u)
             return xn, A, B
         return xn
 
@@ -262,6 +263,85 @@ class L1ControlCost(DeviceCost):
 
     def params(self):
         return np.array([self.h0])
+
+
+# ----------------------------------------------------------------------------------------
+# user-extensible device models: CUDA C++ snippets compiled at run time (NVRTC)
+# ----------------------------------------------------------------------------------------
+class UserDynamics(DeviceDynamics):
+    """Dynamics given as a CUDA C++ snippet  `template <class T> void dynamics(const double* p, const T* x,
+    const T* u, T* xn)`  (include/ratilqr.h, "user-extensible device models").  `py` is an optional host callable
+    `py(p, x, u) -> xn` so that the object is still callable on the CPU like a Julia closure; the solvers never use it."""
+
+    def __init__(self, n, m, src, params=(), py=None):
+        self.model_id, self.n, self.m, self.src, self.py = None, int(n), int(m), src, py
+        self.params = np.asarray(params, dtype=np.float64).reshape(-1)
+        assert self.params.size <= 8, "user dynamics take at most 8 parameters"
+
+    def __call__(self, x, u, f_returns_jacobian=False):
+        if self.py is None:
+            raise TypeError("this UserDynamics has no host callable (pass py=...)")
+        x, u = np.asarray(x, float), np.asarray(u, float)
+        xn = np.asarray(self.py(self.params, x, u), float)
+        if not f_returns_jacobian:
+            return xn
+        h, n, m = 1e-30, self.n, self.m  # complex-step Jacobians, like the registered models
+        A, B = np.zeros((n, n)), np.zeros((n, m))
+        for j in range(n):
+            xc = x.astype(complex); xc[j] += 1j * h
+            A[:, j] = np.imag(self.py(self.params, xc, u.astype(complex))) / h
+        for j in range(m):
+            uc = u.astype(complex); uc[j] += 1j * h
+            B[:, j] = np.imag(self.py(self.params, x.astype(complex), uc)) / h
+        return xn, A, B
+
+
+class UserCost(DeviceCost):
+    """Cost given as a CUDA C++ snippet defining `stage_cost<T>(cp, k, x, u)` and `terminal_cost<T>(cp, x)`;
+    `cp` is the parameter vector.  `stage_py(cp, k, x, u)` / `terminal_py(cp, x)` are optional host callables."""
+
+    cost_id = 100  # RATILQR_COST_USER
+
+    def __init__(self, src, params=(), stage_py=None, terminal_py=None):
+        super().__init__()
+        self.src, self.stage_py, self.terminal_py = src, stage_py, terminal_py
+        self._params = np.asarray(params, dtype=np.float64).reshape(-1)
+
+    def stage(self, k, x, u):
+        if self.stage_py is None:
+            raise TypeError("this UserCost has no host callable (pass stage_py=...)")
+        return float(self.stage_py(self._params, k, x, u))
+
+    def terminal(self, x):
+        if self.terminal_py is None:
+            raise TypeError("this UserCost has no host callable (pass terminal_py=...)")
+        return float(self.terminal_py(self._params, x))
+
+    def params(self):
+        return self._params.copy()
+
+
+def register_user_model(backend, dynamics, cost):
+    """Compile + load a (dynamics, cost) pair of which at least one is user-supplied; returns the dynamics object
+    to put into the problem struct (its model_id now names the compiled pair in `backend`'s context; use it together
+    with `cost.c`, `cost.h`).  `dynamics`: UserDynamics or a registered DeviceDynamics; `cost`: UserCost or a
+    registered DeviceCost."""
+    ud, uc = isinstance(dynamics, UserDynamics), isinstance(cost, UserCost)
+    if not (ud or uc):
+        raise TypeError("neither the dynamics nor the cost is user-supplied: nothing to compile")
+    mid = backend.user_model_register(
+        dynamics.n, dynamics.m,
+        dynamics_src=dynamics.src if ud else None, base_model_id=0 if ud else dynamics.model_id,
+        n_model_params=dynamics.params.size,
+        cost_src=cost.src if uc else None, base_cost_id=0 if uc else cost.cost_id,
+        n_cost_params=cost.params().size if uc else 0)
+    if ud:
+        bound = UserDynamics(dynamics.n, dynamics.m, dynamics.src, dynamics.params, dynamics.py)
+    else:
+        bound = DeviceDynamics(dynamics.model_id, dynamics.params)
+        bound.host_model_id = dynamics.model_id
+    bound.model_id = mid
+    return bound
 
 
 class ConstantCovariance:

@@ -11,9 +11,59 @@
 #include "../../ratilqr.jl_b200/csrc/rl_coop.cuh"
 #include "../../ratilqr.jl_b200/csrc/rl_host.hpp"
 
+#include "../../ratilqr.jl_b200/csrc/rl_user.cuh"
+
 using namespace rl;
 
+// ---- statically compiled copies of the USER-MODEL snippets of tests/user_models/ ---------------------------------
+// The GPU tests hand the same text to NVRTC (ratilqr_user_model_register); here g++ compiles it through the same
+// adapters (rl_user.cuh: UserDyn / UserCost, forward-mode duals), so the user-model arithmetic has a CPU check too.
+// hostemu-only numbering: model 1000 = unicycle snippet, 1001 = drag car; cost 100 = goal cost, 101 = obstacle cost.
+using rl::square;
+namespace um_unicycle {
+#include "../user_models/unicycle_dynamics.inc"
+}
+namespace um_dragcar {
+#include "../user_models/drag_car_dynamics.inc"
+}
+namespace um_goal {
+#include "../user_models/goal_cost.inc"
+}
+namespace um_obstacle {
+#include "../user_models/obstacle_cost.inc"
+}
+struct UmUnicycleBody { template <class T> void operator()(const double* p, const T* x, const T* u, T* xn) const { um_unicycle::dynamics<T>(p, x, u, xn); } };
+struct UmDragCarBody { template <class T> void operator()(const double* p, const T* x, const T* u, T* xn) const { um_dragcar::dynamics<T>(p, x, u, xn); } };
+struct UmGoalFn {
+  template <class T> T stage(const double* cp, int k, const T* x, const T* u) const { return um_goal::stage_cost<T>(cp, k, x, u); }
+  template <class T> T terminal(const double* cp, const T* x) const { return um_goal::terminal_cost<T>(cp, x); }
+};
+struct UmObstacleFn {
+  template <class T> T stage(const double* cp, int k, const T* x, const T* u) const { return um_obstacle::stage_cost<T>(cp, k, x, u); }
+  template <class T> T terminal(const double* cp, const T* x) const { return um_obstacle::terminal_cost<T>(cp, x); }
+};
+typedef UserDyn<4, 2, UmUnicycleBody> UmUnicycle;
+typedef UserDyn<4, 2, UmDragCarBody> UmDragCar;
+typedef UserCost<4, 2, 11, UmGoalFn> UmGoal;
+typedef UserCost<4, 2, 15, UmObstacleFn> UmObstacle;
+
+static const char* hm_check_desc(const ratilqr_problem_desc* d, bool differentiable) {
+  if (d && d->model_id < 1000 && d->cost_id < 100) return rlh::check_desc(d, differentiable);
+  if (!d || d->n != 4 || d->m != 2 || d->N < 1 || !d->W || !d->cost_params) return "bad user-model description";
+  return nullptr;
+}
+
 template <class F> static int dispatch(int model_id, int cost_id, F&& fn) {
+  if (model_id >= 1000 || cost_id >= 100) {
+    using Quad = Cost<RATILQR_COST_QUADRATIC, 4, 2>;
+    if (model_id == 1000 && cost_id == RATILQR_COST_QUADRATIC) { fn(UmUnicycle(), Quad()); return 0; }
+    if (model_id == 1000 && cost_id == 100) { fn(UmUnicycle(), UmGoal()); return 0; }
+    if (model_id == RATILQR_MODEL_UNICYCLE && cost_id == 100) { fn(Dyn<RATILQR_MODEL_UNICYCLE>(), UmGoal()); return 0; }
+    if (model_id == 1000 && cost_id == 101) { fn(UmUnicycle(), UmObstacle()); return 0; }
+    if (model_id == 1001 && cost_id == 101) { fn(UmDragCar(), UmObstacle()); return 0; }
+    if (model_id == 1001 && cost_id == RATILQR_COST_QUADRATIC) { fn(UmDragCar(), Quad()); return 0; }
+    return -5;
+  }
 #define X(MID, CID) if (model_id == MID && cost_id == CID) { fn(Dyn<MID>(), Cost<CID, Dyn<MID>::n, Dyn<MID>::m>()); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)
   RL_FOR_EACH_ROLLOUT_ONLY_COMBO(X)
@@ -50,7 +100,7 @@ int32_t hostemu_set_dynamic(int32_t v) { g_dynamic = v; return 0; }
 
 int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
                                   const ratilqr_batch_in* in, ratilqr_ileqg_out* out) {
-  if (rlh::check_desc(desc, true)) return -1;
+  if (hm_check_desc(desc, true)) return -1;
   const int n = desc->n, m = desc->m, N = desc->N;
   const size_t B = (size_t)in->P * in->K;
   rlh::WPrep wp;
@@ -82,7 +132,7 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
     std::stable_sort(pp, pp + in->K, [&](int32_t a, int32_t b2) { return in->theta[a] < in->theta[b2]; });
   }
   P.perm = in->K >= 2 ? perm.data() : nullptr;
-  const int cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
+  const int cost_id = (desc->model_id < 1000 && rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
   if (g_coop) {
     std::vector<double> xo((size_t)n * (N + 1) * B), lo((size_t)m * N * B), Lo((size_t)m * n * N * B, 0.0);
     P.perm = nullptr; P.xo = xo.data(); P.lo = lo.data(); P.Lo = Lo.data();
@@ -218,7 +268,7 @@ int32_t hostemu_integrate_cost_batch(void*, const ratilqr_problem_desc* d, int32
 int32_t hostemu_linearize_batch(void*, const ratilqr_problem_desc* d, int32_t B, const double* x, const double* u,
                                 double* q, double* qv, double* Q, double* r, double* R, double* Pm, double* A, double* Bm,
                                 int32_t* status) {
-  if (rlh::check_desc(d, true)) return -1;
+  if (hm_check_desc(d, true)) return -1;
   return dispatch(d->model_id, d->cost_id, [&](auto D, auto CT) {
     constexpr int n = decltype(D)::n, m = decltype(D)::m;
     int N = d->N;
