@@ -266,8 +266,9 @@ def main():
         traffic = None  # dram__bytes_read+write of the solve kernel from the committed ncu --set full capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "solve_traffic.json")))
-            if tj.get("problems_per_gpu") == P:
-                traffic = tj["dram_bytes_per_launch"]
+            for ent in tj.get("entries", [tj]):
+                if ent.get("problems_per_gpu") == P:
+                    traffic = ent["dram_bytes_per_launch"]
         except OSError:
             pass
         ach_gbs = byts / (ms_per_step * 1e-3) / 1e9

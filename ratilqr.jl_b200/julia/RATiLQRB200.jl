@@ -104,7 +104,55 @@ function b200_context(device::Integer=0)
 end
 last_error() = unsafe_string(ccall((:ratilqr_last_error, LIB), Cstring, (Ptr{Cvoid},), CTX[]))
 
-is_device(problem) = problem.f isa DeviceDynamics && problem.c isa StageCost && problem.h isa TerminalCost
+# ---- user-extensible device models (include/ratilqr.h: ratilqr_user_model_register) ------------------------------
+# The user keeps the Julia closure for the CPU path and adds a CUDA C++ snippet for the device:
+#   f = UserDeviceDynamics(4, 2, [0.1], src_dynamics, (x, u) -> ...)     # `template <class T> void dynamics(p, x, u, xn)`
+#   c, h = user_cost(4, 2, cp, src_cost, (k, x, u) -> ..., x -> ...)       # stage_cost<T> / terminal_cost<T>
+#   register_user_model!(f, c)      # NVRTC compile + load; afterwards solve!/compute_cost dispatch to the GPU
+mutable struct UserDeviceDynamics <: Function
+    n::Int; m::Int; params::Vector{Float64}; src::String; cpu::Function; model_id::Int32
+end
+UserDeviceDynamics(n, m, params, src, cpu) = UserDeviceDynamics(n, m, Float64.(params), src, cpu, Int32(0))
+(f::UserDeviceDynamics)(x, u, f_returns_jacobian=false) = f.cpu(x, u)
+struct UserStageCost <: Function; id::Int32; params::Vector{Float64}; n::Int; m::Int; src::String; cpu::Function; end
+struct UserTerminalCost <: Function; id::Int32; params::Vector{Float64}; n::Int; m::Int; cpu::Function; end
+(c::UserStageCost)(k, x, u) = c.cpu(k, x, u)
+(h::UserTerminalCost)(x) = h.cpu(x)
+user_cost(n, m, params, src, c_cpu, h_cpu) = (UserStageCost(Int32(100), Float64.(params), n, m, src, c_cpu),
+                                              UserTerminalCost(Int32(100), Float64.(params), n, m, h_cpu))
+struct UserModelDesc
+    n::Int32; m::Int32; dynamics_src::Cstring; base_model_id::Int32; n_model_params::Int32
+    cost_src::Cstring; base_cost_id::Int32; n_cost_params::Int32
+end
+dims_of(f::DeviceDynamics) = MODEL_DIMS[f.model_id]
+dims_of(f::UserDeviceDynamics) = (f.n, f.m)
+
+# f: UserDeviceDynamics or DeviceDynamics; c: UserStageCost or StageCost.  Returns the dynamics object to put into the
+# problem struct (its model_id names the compiled pair inside this process's context).
+function register_user_model!(f, c)
+    ud, uc = f isa UserDeviceDynamics, c isa UserStageCost
+    (ud || uc) || error("neither the dynamics nor the cost is user-supplied")
+    n, m = dims_of(f)
+    dsrc = ud ? f.src : ""; csrc = uc ? c.src : ""
+    log = zeros(UInt8, 1 << 16); id = Ref{Int32}(0)
+    GC.@preserve dsrc csrc log begin
+        um = UserModelDesc(n, m, ud ? Base.unsafe_convert(Cstring, dsrc) : Cstring(C_NULL), ud ? 0 : f.model_id,
+                           length(f.params), uc ? Base.unsafe_convert(Cstring, csrc) : Cstring(C_NULL), uc ? 0 : c.id,
+                           uc ? length(c.params) : 0)
+        rc = ccall((:ratilqr_user_model_register, LIB), Int32, (Ptr{Cvoid}, Ref{UserModelDesc}, Ref{Int32}, Ptr{UInt8}, Int64),
+                   b200_context(), um, id, log, length(log))
+        rc == 0 || error("ratilqr_user_model_register failed ($rc):\n" * unsafe_string(pointer(log)))
+    end
+    if ud
+        f.model_id = id[]
+        return f
+    end
+    return DeviceDynamics(id[], f.params)   # registered dynamics bound to the user cost (CPU evaluation: use `f` itself)
+end
+
+is_device(problem) = (problem.f isa DeviceDynamics || (problem.f isa UserDeviceDynamics && problem.f.model_id != 0)) &&
+                     (problem.c isa StageCost || problem.c isa UserStageCost) &&
+                     (problem.h isa TerminalCost || problem.h isa UserTerminalCost)
 
 opts_of(s::ILEQGSolver) = IleqgOpts(s.μ_min, s.Δ_0, s.λ, s.d, s.iter_max, s.ϵ_init_auto, s.ϵ_init_init, s.ϵ_min, s.f_returns_jacobian)
 
@@ -117,7 +165,7 @@ end
 # batched core: θ vector in, (value, status, x, l, L) out
 function solve_batch(problem, opts::IleqgOpts, x_0::Vector{Float64}, u_array::Vector{Vector{Float64}},
                      θs::Vector{Float64}; want_traj::Bool=true, eps_cap::Int=0)
-    n, m = MODEL_DIMS[problem.f.model_id]; N = problem.N; B = length(θs)
+    n, m = dims_of(problem.f); N = problem.N; B = length(θs)
     U = reduce(hcat, u_array)                        # m x N, column-major
     Ws = [Matrix{Float64}(problem.W(k)) for k in 0:N-1]
     tv = any(w != Ws[1] for w in Ws)

@@ -54,7 +54,7 @@ static const char* hm_check_desc(const ratilqr_problem_desc* d, bool differentia
 }
 
 template <class F> static int dispatch(int model_id, int cost_id, F&& fn) {
-  if (model_id >= 1000 || cost_id >= 100) {
+  if (model_id >= 1000 || cost_id == 100 || cost_id == 101) {  // (RL_COST_QUAD_DIAG is 0x101: not a user id)
     using Quad = Cost<RATILQR_COST_QUADRATIC, 4, 2>;
     if (model_id == 1000 && cost_id == RATILQR_COST_QUADRATIC) { fn(UmUnicycle(), Quad()); return 0; }
     if (model_id == 1000 && cost_id == 100) { fn(UmUnicycle(), UmGoal()); return 0; }
