@@ -229,12 +229,35 @@ int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, i
                            int32_t n_samples, const double* noise, uint64_t seed,
                            double theta_risk, double* J, double* stats, double* x_out);
 
+/* "True model" process noise: a Gaussian mixture  sum_c weights[c] N(means[:,c], covs[:,:,c])
+ * -- the accurate GMM of the reference's generative example, selected there by
+ * f_stochastic(x, u, rng, use_true_model=true) (src/optimal_control_problems.jl:85-86,
+ * 102-115), against the single Gaussian the planner assumes. */
+typedef struct {
+  int32_t n_components;   /* >= 1 */
+  const double* weights;  /* n_components, > 0 (normalised by the library) */
+  const double* means;    /* n * n_components, column-major */
+  const double* covs;     /* n*n * n_components, each positive definite */
+} ratilqr_noise_mixture;
+/* Closed-loop Monte Carlo evaluation under the TRUE noise model: same as
+ * ratilqr_mc_rollout in Philox mode, but w_k is drawn from `true_noise` instead of N(0, W(k)):
+ * E[J], Var[J] and the entropic risk of a policy that was optimised under the Gaussian model. */
+int32_t ratilqr_mc_rollout_true_model(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t P,
+                                      const double* xbar, const double* l, const double* L,
+                                      int32_t n_samples, const ratilqr_noise_mixture* true_noise,
+                                      uint64_t seed, double theta_risk, double* J, double* stats,
+                                      double* x_out);
+
 /* ---- PETS (pets.jl) ---------------------------------------------------------------- */
 typedef struct {
   int32_t noise_kind;       /* 0 gaussian chol(W)*z ; 1 uniform[0,1)*scale (test/pets_test.jl:15) */
   double  noise_scale;
   int32_t n_ensemble;       /* model parameter sets; particle kk uses set kk / (particles/n_ensemble) */
   const double* ensemble_params; /* n_model_params * n_ensemble, or NULL -> desc.model_params */
+  /* f_stochastic(x, u, rng, use_true_model) (optimal_control_problems.jl:82-87): when use_true_model != 0
+   * and true_model != NULL, on-device (Philox) noise is drawn from the mixture instead of noise_kind */
+  const ratilqr_noise_mixture* true_model;
+  int32_t use_true_model;
 } ratilqr_generative_desc;
 
 /* compute_cost_serial (pets.jl:128-157): controls m*N*C, noise n*N*particles*C or NULL->Philox */

@@ -53,10 +53,15 @@ class IleqgOut(C.Structure):  # ratilqr_ileqg_out
     ]
 
 
+class NoiseMixture(C.Structure):  # ratilqr_noise_mixture
+    _fields_ = [("n_components", C.c_int32), ("weights", c_double_p), ("means", c_double_p), ("covs", c_double_p)]
+
+
 class GenerativeDesc(C.Structure):  # ratilqr_generative_desc
     _fields_ = [
         ("noise_kind", C.c_int32), ("noise_scale", C.c_double),
         ("n_ensemble", C.c_int32), ("ensemble_params", c_double_p),
+        ("true_model", C.POINTER(NoiseMixture)), ("use_true_model", C.c_int32),
     ]
 
 
@@ -173,6 +178,8 @@ class CApi:
         self.f_ric = self._fn("riccati_batch", [vp, i32, i32, i32, i32, i32] + [dp] * 8 + [dp, dp, f64, f64, dp, dp,
                                                                                           dp, dp, dp, dp, dp, ip, ip])
         self.f_mc = self._fn("mc_rollout", [vp, PD, i32, dp, dp, dp, i32, dp, C.c_uint64, f64, dp, dp, dp])
+        self.f_mc_true = self._fn("mc_rollout_true_model", [vp, PD, i32, dp, dp, dp, i32, C.POINTER(NoiseMixture), C.c_uint64,
+                                                            f64, dp, dp, dp])
         self.f_pets_costs = self._fn("pets_costs", [vp, PD, GD, dp, dp, i32, i32, dp, C.c_uint64, dp])
         self.f_pets_refit = self._fn("pets_refit", [vp, i32, i32, i32, i32, f64, dp, dp, dp, dp, ip])
         self.f_ce_fleet = self._fn("ce_solve_fleet", [vp, PD, IO, C.POINTER(CeOpts), i32, dp, i32, dp, i32, f64, dp, C.c_int64,
@@ -504,13 +511,39 @@ class CApi:
         return dict(J=J, stats=stats.reshape(P, 3), x=xo)
 
     @staticmethod
-    def _gen(gen):
+    def _mixture(mix):
+        """mix: dict(weights (k,), means (n, k), covs (n, n, k)) -> (NoiseMixture, keep-alive buffers)"""
+        w = _f64(mix["weights"])
+        mu = _f64(np.asarray(mix["means"], dtype=np.float64).reshape(-1, w.size))
+        cv = _f64(np.asarray(mix["covs"], dtype=np.float64).reshape(mu.size // w.size, -1, w.size))
+        return NoiseMixture(int(w.size), _dp(w), _dp(mu), _dp(cv)), (w, mu, cv)
+
+    def mc_rollout_true_model(self, spec, xbar, l, L, n_samples, mixture, seed=0, theta_risk=0.0, want_x=False, P=1):
+        """closed-loop MC evaluation under the true (Gaussian-mixture) noise model"""
+        n, N = spec.n, spec.N
+        xf, lf, Lf = _f64(xbar), _f64(l), _f64(L)
+        J = np.zeros(n_samples * P)
+        stats = np.zeros(3 * P)
+        xo = np.zeros((n, N + 1, n_samples * P), order="F") if want_x else None
+        d = spec.desc()
+        mx, keep = self._mixture(mixture)
+        self._check(self.f_mc_true(self.ctx, C.byref(d), P, _dp(xf), _dp(lf), _dp(Lf), n_samples, C.byref(mx), int(seed),
+                                   float(theta_risk), _dp(J), _dp(stats), _dp(xo)), "mc_rollout_true_model")
+        return dict(J=J, stats=stats.reshape(P, 3), x=xo)
+
+    def _gen(self, gen):
         gen = gen or {}
         ens = gen.get("ensemble_params")
         ensf = None if ens is None else _f64(ens)
+        keep = [ensf]
         g = GenerativeDesc(int(gen.get("noise_kind", 0)), float(gen.get("noise_scale", 1.0)),
-                           int(gen.get("n_ensemble", 1)), _dp(ensf))
-        return g, ensf
+                           int(gen.get("n_ensemble", 1)), _dp(ensf), None, 0)
+        if gen.get("use_true_model") and gen.get("true_model") is not None:
+            mx, bufs = self._mixture(gen["true_model"])
+            keep += [mx, bufs]
+            g.true_model = C.pointer(mx)
+            g.use_true_model = 1
+        return g, keep
 
     def pets_costs(self, spec, x0, controls, particles, noise=None, seed=0, gen=None):
         """compute_cost_serial (pets.jl:128-157). controls (m, N, C)."""

@@ -3,7 +3,7 @@
 // (user-extensible device models, rl_user.cuh), so a block filled on the host has the layout the kernel expects.
 // All pointers are DEVICE pointers.
 #pragma once
-#include "rl_core.cuh"
+#include "rl_components.cuh"
 
 namespace rll {
 
@@ -26,6 +26,7 @@ struct McArgs {
   const double* noise;               // n*N*n_samples*P or null
   const double* cholW; int W_tv;     // n*n [*N]
   uint64_t seed;
+  rl::MixtureView mix;               // true-model noise (Philox mode) when mix.k > 0
   double* J; double* x_out;
 };
 
@@ -40,6 +41,7 @@ struct PetsArgs {
   const double* cholW;
   int noise_kind; double noise_scale;
   uint64_t seed; uint64_t stream_offset;
+  rl::MixtureView mix;     // use_true_model: mixture noise when mix.k > 0
   double* cost;            // C
 };
 

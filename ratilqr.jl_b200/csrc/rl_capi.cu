@@ -56,6 +56,7 @@ struct ratilqr_ctx {
   const rlu::Module* staged_user = nullptr;
   // scratch for component calls
   DBuf s[16];
+  DBuf d_mix[3];  // true-model noise mixture: cumulative weights, means, Cholesky factors
   DBuf d_cost;
 };
 
@@ -395,6 +396,7 @@ int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
                  &ctx->d_out3, &ctx->d_cost, &ctx->d_coop_traj, &ctx->d_queue};
   for (DBuf* b : all) b->release();
   for (DBuf& b : ctx->s) b.release();
+  for (DBuf& b : ctx->d_mix) b.release();
   for (rlu::Module* um : ctx->user_models) { rlu::unload(*um); delete um; }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -509,6 +511,19 @@ int32_t ratilqr_ce_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, con
   CU(cudaMemcpyAsync(cost, ctx->d_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CU(cudaMemcpyAsync(status, ctx->sp.status, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// true-model noise mixture -> device view (rl::MixtureView); k = 0 when mx is null
+static int upload_mixture(ratilqr_ctx* ctx, int n, const ratilqr_noise_mixture* mx, rl::MixtureView& v) {
+  v.k = 0; v.cumw = v.mean = v.chol = nullptr;
+  if (!mx) return 0;
+  rlh::MixPrep mp;
+  if (const char* msg = rlh::prep_mixture(n, mx, mp)) FAIL(-2, msg);
+  UP(ctx->d_mix[0], mp.cumw.data(), mp.cumw.size() * 8);
+  UP(ctx->d_mix[1], mp.mean.data(), mp.mean.size() * 8);
+  UP(ctx->d_mix[2], mp.chol.data(), mp.chol.size() * 8);
+  v.k = mp.k; v.cumw = ctx->d_mix[0].as<double>(); v.mean = ctx->d_mix[1].as<double>(); v.chol = ctx->d_mix[2].as<double>();
   return 0;
 }
 
@@ -656,9 +671,10 @@ int32_t ratilqr_riccati_batch(ratilqr_ctx* ctx, int32_t n_, int32_t m_, int32_t 
   return 0;
 }
 
-int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t P, const double* xbar,
-                           const double* l, const double* L, int32_t n_samples, const double* noise, uint64_t seed,
-                           double theta_risk, double* J, double* stats, double* x_out) {
+static int mc_rollout_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t P, const double* xbar,
+                               const double* l, const double* L, int32_t n_samples, const double* noise,
+                               const ratilqr_noise_mixture* true_noise, uint64_t seed, double theta_risk, double* J,
+                               double* stats, double* x_out) {
   if (!ctx) return -1;
   const rlu::Module* um = nullptr;
   if (const char* msg = check_desc_ctx(ctx, desc, false, &um)) FAIL(-1, msg);
@@ -680,6 +696,7 @@ int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, i
   if (noise) { UP(ctx->s[3], noise, n * N * S * 8); a.noise = ctx->s[3].as<double>(); }
   UP(ctx->s[4], wp.cholW.data(), wp.cholW.size() * 8);
   a.cholW = ctx->s[4].as<double>(); a.W_tv = desc->W_time_varying; a.seed = seed;
+  if (int rc = upload_mixture(ctx, desc->n, true_noise, a.mix)) return rc;
   CU(ctx->s[5].reserve(S * 8)); a.J = ctx->s[5].as<double>();
   if (x_out) { CU(ctx->s[6].reserve(n * (N + 1) * S * 8)); a.x_out = ctx->s[6].as<double>(); }
   if (um) { if (int rc = user_launch(ctx, um, rlu::K_MC_ROLLOUT, RL_GRID(a.n_samples, 128), (unsigned)a.P, 128, 0, &a, "k_mc_rollout")) return rc; }
@@ -695,6 +712,21 @@ int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, i
   DOWNSYNC(x_out, a.x_out, n * (N + 1) * S * 8);
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t P, const double* xbar,
+                           const double* l, const double* L, int32_t n_samples, const double* noise, uint64_t seed,
+                           double theta_risk, double* J, double* stats, double* x_out) {
+  return mc_rollout_internal(ctx, desc, P, xbar, l, L, n_samples, noise, nullptr, seed, theta_risk, J, stats, x_out);
+}
+
+int32_t ratilqr_mc_rollout_true_model(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int32_t P, const double* xbar,
+                                      const double* l, const double* L, int32_t n_samples,
+                                      const ratilqr_noise_mixture* true_noise, uint64_t seed, double theta_risk,
+                                      double* J, double* stats, double* x_out) {
+  if (!ctx) return -1;
+  if (!true_noise) FAIL(-1, "true_noise is null");
+  return mc_rollout_internal(ctx, desc, P, xbar, l, L, n_samples, nullptr, true_noise, seed, theta_risk, J, stats, x_out);
 }
 
 static int pets_launch_costs(ratilqr_ctx* ctx, const rlu::Module* um, rll::PetsArgs& a) {
@@ -731,6 +763,7 @@ static int pets_fill(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const r
   a.x0 = ctx->s[9].as<double>();
   UP(ctx->s[10], wp.cholW.data(), wp.cholW.size() * 8);
   a.cholW = ctx->s[10].as<double>();
+  if (int rc = upload_mixture(ctx, desc->n, (gen && gen->use_true_model) ? gen->true_model : nullptr, a.mix)) return rc;
   return 0;
 }
 

@@ -238,11 +238,30 @@ RL_HD void philox_noise(uint64_t seed, uint64_t stream, uint32_t step, int kind,
   }
 }
 
+// "true model" noise: Gaussian mixture (optimal_control_problems.jl:105-109).  cumw: cumulative normalised weights,
+// mean n*k, chol n*n*k (lower factors), prepared on the host (rlh::prep_mixture).  The component index consumes its
+// own Philox counter lane, so the normals of a step are the same draws the Gaussian model would use.
+struct MixtureView { int k; const double* cumw; const double* mean; const double* chol; };
+template <int n>
+RL_HD void philox_mixture_noise(uint64_t seed, uint64_t stream, uint32_t step, const MixtureView& mx, double* w) {
+  const double uu = philox_uniform(seed, stream, step, 0xFFFFu, 0);
+  int c = 0;
+  while (c < mx.k - 1 && uu >= mx.cumw[c]) ++c;
+  double z[n + 1];
+  for (int i = 0; i < n; i += 2) philox_normal2(seed, stream, step, (uint32_t)(i >> 1), &z[i], &z[i + 1]);
+  const double* C = mx.chol + (size_t)c * n * n;
+  for (int i = 0; i < n; ++i) {
+    double a = mx.mean[(size_t)c * n + i];
+    for (int k = 0; k <= i; ++k) a = rl_fma(C[i + k * n], z[k], a);
+    w[i] = a;
+  }
+}
+
 // one PETS particle: compute_cost_serial's inner loops for (sequence ii, particle kk) (pets.jl:141-152)
 template <class D, class CT>
 RL_HD double comp_pets_particle(const double* mp, const double* cp, int N, const double* x0, const double* useq,
                                 const double* w /*n*N or null*/, uint64_t seed, uint64_t stream, int noise_kind,
-                                double noise_scale, const double* cholW) {
+                                double noise_scale, const double* cholW, const MixtureView* mx = nullptr) {
   constexpr int n = D::n, m = D::m;
   double x[n], xn[n], u[m], wk[n];
   for (int i = 0; i < n; ++i) x[i] = x0[i];
@@ -254,6 +273,7 @@ RL_HD double comp_pets_particle(const double* mp, const double* cp, int N, const
     c += q;
     if (!D::f(mp, x, u, xn)) return rl_inf();
     if (w) { for (int i = 0; i < n; ++i) wk[i] = w[(size_t)tt * n + i]; }
+    else if (mx && mx->k > 0) philox_mixture_noise<n>(seed, stream, (uint32_t)tt, *mx, wk);
     else philox_noise<n>(seed, stream, (uint32_t)tt, noise_kind, noise_scale, cholW, wk);
     for (int i = 0; i < n; ++i) x[i] = xn[i] + wk[i];
   }

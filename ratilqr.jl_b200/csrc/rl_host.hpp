@@ -67,6 +67,27 @@ inline bool prep_W(int n, int N, const double* W, int time_varying, WPrep& o) {
   return true;
 }
 
+// true-model noise mixture -> cumulative normalised weights + lower Cholesky factors; nullptr if fine, else a message
+struct MixPrep { std::vector<double> cumw, mean, chol; int k = 0; };
+inline const char* prep_mixture(int n, const ratilqr_noise_mixture* mx, MixPrep& o) {
+  if (!mx || mx->n_components < 1 || !mx->weights || !mx->means || !mx->covs) return "bad noise mixture";
+  o.k = mx->n_components;
+  double tot = 0.0;
+  for (int c = 0; c < o.k; ++c) { if (!(mx->weights[c] > 0.0)) return "mixture weights must be positive"; tot += mx->weights[c]; }
+  o.cumw.resize(o.k);
+  double acc = 0.0;
+  for (int c = 0; c < o.k; ++c) { acc += mx->weights[c] / tot; o.cumw[c] = acc; }
+  o.cumw[o.k - 1] = 1.0;
+  o.mean.assign(mx->means, mx->means + (size_t)n * o.k);
+  o.chol.assign((size_t)n * n * o.k, 0.0);
+  std::vector<double> invd(n);
+  double det;
+  for (int c = 0; c < o.k; ++c)
+    if (!chol_lower_host(n, mx->covs + (size_t)c * n * n, &o.chol[(size_t)c * n * n], invd.data(), &det))
+      return "a mixture covariance is not positive definite";
+  return nullptr;
+}
+
 inline bool model_dims(int id, int* n, int* m, int* np) {
   switch (id) {
     case RATILQR_MODEL_SINGLE_INTEGRATOR: *n = 2; *m = 2; *np = 1; return true;

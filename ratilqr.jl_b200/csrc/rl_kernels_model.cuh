@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(128) k_mc_rollout(McArgs a) {
       if (!CT::stage(cp, k, x, u, false, q, nullptr, nullptr, nullptr, nullptr, nullptr)) { st = RATILQR_ST_DOMAIN; break; }
       J += q;
       if (!D::f(a.mp, x, u, xn)) { st = RATILQR_ST_DOMAIN; break; }
-      philox_noise<n>(a.seed, gi, (uint32_t)k, 0, 1.0, a.cholW + (a.W_tv ? (size_t)k * n * n : 0), w);
+      if (a.mix.k > 0) philox_mixture_noise<n>(a.seed, gi, (uint32_t)k, a.mix, w);
+      else philox_noise<n>(a.seed, gi, (uint32_t)k, 0, 1.0, a.cholW + (a.W_tv ? (size_t)k * n * n : 0), w);
       for (int i = 0; i < n; ++i) { x[i] = xn[i] + w[i]; if (a.x_out) a.x_out[gi * n * (N + 1) + (size_t)(k + 1) * n + i] = x[i]; }
     }
     if (!st) {
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(256) k_pets_costs(PetsArgs a) {
     size_t gi = (size_t)ii * a.particles + kk;
     double c = comp_pets_particle<D, CT>(mpp, a.cp, a.N, a.x0, a.controls + (size_t)ii * m * a.N,
                                          a.noise ? a.noise + gi * n * a.N : nullptr, a.seed, a.stream_offset + gi,
-                                         a.noise_kind, a.noise_scale, a.cholW);
+                                         a.noise_kind, a.noise_scale, a.cholW, &a.mix);
     acc += c;
   }
   double tot = block_reduce(acc, OpAdd(), 0.0, sh);

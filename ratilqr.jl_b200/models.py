@@ -360,21 +360,33 @@ class DeviceStochasticDynamics:
     (test/pets_test.jl:15).  An ensemble is a list of parameter sets; the particle index
     selects the member."""
 
-    def __init__(self, dynamics, W=None, noise_kind=0, noise_scale=1.0, ensemble_params=None):
+    def __init__(self, dynamics, W=None, noise_kind=0, noise_scale=1.0, ensemble_params=None, true_mixture=None):
         self.dynamics, self.noise_kind, self.noise_scale = dynamics, int(noise_kind), float(noise_scale)
         n = dynamics.n
         self.W = np.eye(n) if W is None else np.asarray(W, float)
         self.ensemble_params = None if ensemble_params is None else np.asarray(ensemble_params, float)
+        # the accurate model behind `use_true_model=true` (optimal_control_problems.jl:105-109): a Gaussian mixture
+        # dict(weights (k,), means (n, k), covs (n, n, k)); None -> the planner's model is also the true one
+        self.true_mixture = true_mixture
 
     def __call__(self, x, u, rng, use_true_model=False):
         xn = self.dynamics(x, u)
+        if use_true_model and self.true_mixture is not None:
+            w = np.asarray(self.true_mixture["weights"], float)
+            c = int(np.searchsorted(np.cumsum(w / w.sum()), rng.random(), side="right"))
+            c = min(c, w.size - 1)
+            mu = np.asarray(self.true_mixture["means"], float).reshape(xn.size, -1)[:, c]
+            cov = np.asarray(self.true_mixture["covs"], float).reshape(xn.size, xn.size, -1)[:, :, c]
+            return xn + mu + np.linalg.cholesky(cov) @ rng.standard_normal(xn.size)
         if self.noise_kind == 1:
             return xn + self.noise_scale * rng.random(xn.size)
         return xn + np.linalg.cholesky(self.W) @ rng.standard_normal(xn.size)
 
-    def gen(self):
+    def gen(self, use_true_model=False):
         g = dict(noise_kind=self.noise_kind, noise_scale=self.noise_scale, n_ensemble=1)
         if self.ensemble_params is not None:
             g["n_ensemble"] = self.ensemble_params.shape[0]
             g["ensemble_params"] = np.ascontiguousarray(self.ensemble_params).reshape(-1)
+        if use_true_model and self.true_mixture is not None:
+            g["use_true_model"], g["true_model"] = True, self.true_mixture
         return g

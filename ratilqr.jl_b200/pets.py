@@ -43,16 +43,19 @@ def _controls(control_sequence_array):  # Vector{Vector{Vector}} -> (m, N, C)
     return np.stack([_stack(seq) for seq in control_sequence_array], axis=-1)
 
 
-def _noise_for(problem, s, rng, C):
+def _noise_for(problem, s, rng, C, use_true_model=False):
     """Noise tensor (n, N, particles, C) in the reference's consumption order ii -> kk -> tt (pets.jl:137-152)."""
     fs = problem.f_stochastic
     n, N, Kp = fs.dynamics.n, s.N, s.num_trajectory_samples
     w = np.zeros((n, N, Kp, C))
     chol = np.linalg.cholesky(fs.W) if fs.noise_kind == 0 else None
+    zero = np.zeros(n)
     for ii in range(C):
         for kk in range(Kp):
             for tt in range(N):
-                if fs.noise_kind == 1:
+                if use_true_model and fs.true_mixture is not None:  # additive: f_stochastic(0-dynamics) draws the noise
+                    w[:, tt, kk, ii] = fs(zero, np.zeros(fs.dynamics.m), rng, True) - fs.dynamics(zero, np.zeros(fs.dynamics.m))
+                elif fs.noise_kind == 1:
                     w[:, tt, kk, ii] = fs.noise_scale * rng.random(n)
                 else:
                     w[:, tt, kk, ii] = chol @ rng.standard_normal(n)
@@ -66,10 +69,11 @@ def compute_cost_serial(s, problem, x, control_sequence_array, rng, use_true_mod
     assert all(len(seq) == s.N for seq in control_sequence_array)
     C = s.num_control_samples
     if noise is None and rng is not None and not isinstance(rng, int):
-        noise = _noise_for(problem, s, rng, C)
+        noise = _noise_for(problem, s, rng, C, use_true_model)
     seed = rng if isinstance(rng, int) else 0
     return s._be().pets_costs(problem.spec(), np.asarray(x, float), _controls(control_sequence_array),
-                              s.num_trajectory_samples, noise=noise, seed=seed, gen=problem.f_stochastic.gen())
+                              s.num_trajectory_samples, noise=noise, seed=seed,
+                              gen=problem.f_stochastic.gen(use_true_model))
 
 
 def compute_cost(s, problem, x, control_sequence_array, rng, use_true_model=False, noise=None):
@@ -126,11 +130,11 @@ def solve_(s, problem, x_0, rng, use_true_model=False, verbose=False, serial=Tru
             for ii in range(C):
                 for tt in range(N):
                     z_inject[:, tt, ii, it] = rng.standard_normal(m)
-            noise[..., it] = _noise_for(problem, s, rng, C)
+            noise[..., it] = _noise_for(problem, s, rng, C, use_true_model)
     mu, Sg = s._be().pets_solve(problem.spec(), np.asarray(x_0, float), _stack(s.mu_array), _stack(s.Sigma_array),
                                 s.num_control_samples, s.num_trajectory_samples, s.num_elite, s.iter_max,
                                 s.smoothing_factor, z_inject=z_inject, noise=noise, seed=seed,
-                                gen=problem.f_stochastic.gen())
+                                gen=problem.f_stochastic.gen(use_true_model))
     s.mu_array, s.Sigma_array = _cols(mu), _mats(Sg)
     s.iter_current = s.iter_max
     return [v.copy() for v in s.mu_array], [v.copy() for v in s.Sigma_array]

@@ -299,11 +299,17 @@ int32_t hostemu_riccati_batch(void*, int32_t n, int32_t m, int32_t N, int32_t B,
   return -5;
 }
 
-int32_t hostemu_mc_rollout(void*, const ratilqr_problem_desc* d, int32_t P, const double* xbar, const double* l,
-                           const double* L, int32_t n_samples, const double* noise, uint64_t seed, double, double* J,
-                           double* stats, double* x_out) {
+static int32_t mc_rollout_impl(const ratilqr_problem_desc* d, int32_t P, const double* xbar, const double* l,
+                              const double* L, int32_t n_samples, const double* noise, const ratilqr_noise_mixture* true_noise,
+                              uint64_t seed, double* J, double* stats, double* x_out) {
   rlh::WPrep wp;
   if (!rlh::prep_W(d->n, d->N, d->W, d->W_time_varying, wp)) return -2;
+  rlh::MixPrep mp;
+  MixtureView mx{0, nullptr, nullptr, nullptr};
+  if (true_noise) {
+    if (rlh::prep_mixture(d->n, true_noise, mp)) return -2;
+    mx = MixtureView{mp.k, mp.cumw.data(), mp.mean.data(), mp.chol.data()};
+  }
   return dispatch(d->model_id, d->cost_id, [&](auto D, auto CT) {
     constexpr int n = decltype(D)::n, m = decltype(D)::m;
     int N = d->N;
@@ -314,6 +320,7 @@ int32_t hostemu_mc_rollout(void*, const ratilqr_problem_desc* d, int32_t P, cons
         double c = HUGE_VAL;
         std::vector<double> w((size_t)n * N);
         if (noise) memcpy(w.data(), noise + gi * n * N, sizeof(double) * n * N);
+        else if (mx.k > 0) for (int k = 0; k < N; ++k) philox_mixture_noise<n>(seed, gi, (uint32_t)k, mx, &w[(size_t)k * n]);
         else for (int k = 0; k < N; ++k) philox_noise<n>(seed, gi, (uint32_t)k, 0, 1.0, wp.cholW.data() + (d->W_time_varying ? (size_t)k * n * n : 0), &w[(size_t)k * n]);
         int st = comp_rollout_closed<decltype(D), decltype(CT)>(d->model_params, cp, N, xbar + (size_t)p * n * (N + 1), l + (size_t)p * m * N,
                                                                L + (size_t)p * m * n * N, w.data(),
@@ -324,11 +331,28 @@ int32_t hostemu_mc_rollout(void*, const ratilqr_problem_desc* d, int32_t P, cons
   });
 }
 
+int32_t hostemu_mc_rollout(void*, const ratilqr_problem_desc* d, int32_t P, const double* xbar, const double* l,
+                           const double* L, int32_t n_samples, const double* noise, uint64_t seed, double, double* J,
+                           double* stats, double* x_out) {
+  return mc_rollout_impl(d, P, xbar, l, L, n_samples, noise, nullptr, seed, J, stats, x_out);
+}
+int32_t hostemu_mc_rollout_true_model(void*, const ratilqr_problem_desc* d, int32_t P, const double* xbar, const double* l,
+                                      const double* L, int32_t n_samples, const ratilqr_noise_mixture* true_noise,
+                                      uint64_t seed, double, double* J, double* stats, double* x_out) {
+  return mc_rollout_impl(d, P, xbar, l, L, n_samples, nullptr, true_noise, seed, J, stats, x_out);
+}
+
 int32_t hostemu_pets_costs(void*, const ratilqr_problem_desc* d, const ratilqr_generative_desc* gen, const double* x0,
                            const double* controls, int32_t C, int32_t particles, const double* noise, uint64_t seed,
                            double* cost) {
   rlh::WPrep wp;
   if (!rlh::prep_W(d->n, d->N, d->W, 0, wp)) return -2;
+  rlh::MixPrep mp;
+  MixtureView mx{0, nullptr, nullptr, nullptr};
+  if (gen && gen->use_true_model && gen->true_model) {
+    if (rlh::prep_mixture(d->n, gen->true_model, mp)) return -2;
+    mx = MixtureView{mp.k, mp.cumw.data(), mp.mean.data(), mp.chol.data()};
+  }
   return dispatch(d->model_id, d->cost_id, [&](auto D, auto CT) {
     constexpr int n = decltype(D)::n, m = decltype(D)::m;
     int N = d->N;
@@ -342,7 +366,7 @@ int32_t hostemu_pets_costs(void*, const ratilqr_problem_desc* d, const ratilqr_g
         size_t gi = (size_t)ii * particles + kk;
         acc += comp_pets_particle<decltype(D), decltype(CT)>(mp, d->cost_params, N, x0, controls + (size_t)ii * m * N,
                                                             noise ? noise + gi * n * N : nullptr, seed, gi,
-                                                            gen ? gen->noise_kind : 0, gen ? gen->noise_scale : 1.0, wp.cholW.data());
+                                                            gen ? gen->noise_kind : 0, gen ? gen->noise_scale : 1.0, wp.cholW.data(), &mx);
       }
       cost[ii] = acc / particles;
     }
