@@ -3,10 +3,13 @@
 // There is no CPU compute path in this file: every entry point ends in a kernel launch.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rl_host.hpp"
@@ -54,6 +57,13 @@ struct ratilqr_ctx {
   // user-extensible device models (NVRTC): id = RATILQR_MODEL_USER_BASE + index
   std::vector<rlu::Module*> user_models;
   const rlu::Module* staged_user = nullptr;
+  // sub-fleet contexts (own stream + buffers) for the concurrent fleet solve; they resolve user models through `parent`
+  std::vector<ratilqr_ctx*> children;
+  const ratilqr_ctx* parent = nullptr;
+  std::vector<int32_t> fleet_key;  // per-problem work of the last fleet round (slot ordering across rounds and MPC steps)
+  DBuf d_order, d_key;
+  int32_t* h_key = nullptr;        // pinned
+  int h_key_cap = 0, profile_pending = 0;
   // scratch for component calls
   DBuf s[16];
   DBuf d_mix[3];  // true-model noise mixture: cumulative weights, means, Cholesky factors
@@ -105,8 +115,42 @@ __global__ void k_ce_cost(int B, const double* value, const int32_t* status, con
   cost[b] = status[b] == 0 ? value[b] + kl / theta[b] : HUGE_VAL;
 }
 
+// ---- work profile: per-problem iteration counts of the last launch, used to order the next one ----------------------
+// The number of iLEQG iterations is a property of the PROBLEM (x0, goal) far more than of theta, and the bilevel
+// optimisers call the batched solve again and again on the same problems with fresh theta populations (one call per
+// CE iteration, cross_entropy_bilevel_optimization.jl:291-334; one fleet solve per MPC step).  So the iterations each
+// problem needed last time predict what it needs now (round-to-round correlation 0.95 on the C5 fleet), and laying the
+// problems out heaviest-first removes the launch tail formed by the ~5 % that run to iter_max (list scheduling:
+// makespan 1.06x ideal in natural order, 1.001x heaviest-first).  Pure scheduling: results do not depend on it.
+// RATILQR_PROFILE_ORDER=0 disables it.
+static bool profile_enabled() {
+  static const bool on = [] { const char* e = getenv("RATILQR_PROFILE_ORDER"); return !(e && e[0] == '0'); }();
+  return on;
+}
+// enqueue: key[p] = max iterations of problem p -> pinned host buffer; valid after the caller's next stream sync
+static int work_profile_enqueue(ratilqr_ctx* ctx, int P, int K) {
+  if (P < 64 || !profile_enabled() || ctx->coop) { ctx->profile_pending = 0; return 0; }
+  CU(ctx->d_key.reserve((size_t)P * 4));
+  if (ctx->h_key_cap < P) {
+    if (ctx->h_key) cudaFreeHost(ctx->h_key);
+    ctx->h_key = nullptr; ctx->h_key_cap = 0;
+    CU(cudaMallocHost(&ctx->h_key, (size_t)P * 4));
+    ctx->h_key_cap = P;
+  }
+  rll::launch_problem_work(ctx->sp.iters, P, K, ctx->d_key.as<int32_t>(), ctx->stream);
+  if (int rc = check_launch(ctx, "k_problem_work")) return rc;
+  CU(cudaMemcpyAsync(ctx->h_key, ctx->d_key.p, (size_t)P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->profile_pending = P;
+  return 0;
+}
+static void work_profile_commit(ratilqr_ctx* ctx) {  // after a stream synchronisation
+  if (ctx->profile_pending > 0) ctx->fleet_key.assign(ctx->h_key, ctx->h_key + ctx->profile_pending);
+  ctx->profile_pending = 0;
+}
+
 // ---- user-extensible device models: lookup, validation, launch ------------------------------------------------
 static const rlu::Module* find_user(const ratilqr_ctx* ctx, int model_id) {
+  if (ctx->parent) ctx = ctx->parent;
   const int i = model_id - RATILQR_MODEL_USER_BASE;
   return (i >= 0 && i < (int)ctx->user_models.size()) ? ctx->user_models[i] : nullptr;
 }
@@ -203,7 +247,18 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   { const char* e = getenv("RATILQR_NO_STAGE"); P.use_stage = (e && e[0] == '1') ? 0 : 1; }
   // warp-homogeneous scheduling: lanes of a warp get neighbouring theta of one problem
   CU(ctx->d_perm.reserve(B * 4));
-  if (!device_theta && rll::launch_sort_theta(P.theta, in->P, in->K, ctx->d_perm.as<int32_t>(), ctx->stream) == 0) {
+  // ... and, when the previous call solved a fleet of this many problems, problems go heaviest-first (work_profile below)
+  const int32_t* order = nullptr;
+  if (!device_theta && (int)ctx->fleet_key.size() == in->P && in->P >= 64 && profile_enabled()) {
+    std::vector<int32_t> ord(in->P);
+    std::iota(ord.begin(), ord.end(), 0);
+    const std::vector<int32_t>& key = ctx->fleet_key;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key[a] > key[b]; });
+    UP(ctx->d_order, ord.data(), (size_t)in->P * 4);
+    CU(cudaStreamSynchronize(ctx->stream));  // ord is a stack vector
+    order = ctx->d_order.as<int32_t>();
+  }
+  if (!device_theta && rll::launch_sort_theta(P.theta, in->P, in->K, order, ctx->d_perm.as<int32_t>(), ctx->stream) == 0) {
     if (int rc = check_launch(ctx, "k_sort_theta")) return rc;
     P.perm = ctx->d_perm.as<int32_t>();
   } else {
@@ -293,23 +348,36 @@ static int run_internal(ratilqr_ctx* ctx, int reps, float* ms_total) {
 // Fleet scheduling: order the thread slots by the work each PROBLEM needed in the previous launch (max iterations
 // over its instances), so that the 32 lanes of a warp hold problems of similar length.  Host-side argsort of P keys
 // (the fleet loop synchronises once per round anyway).
-#include <algorithm>
-#include <numeric>
-static int resort_slots_by_last_iters(ratilqr_ctx* ctx, int P, int K) {
+// slot r*K + j <- instance order[r]*K + j, problems ordered by `key` (their predicted work), HEAVIEST FIRST: CTAs are
+// dispatched in grid order, so the few problems that run to iter_max (the mu quirk of ileqg.jl:471-488; ~5 % of a
+// fleet, 5x the median work) start with the launch instead of forming its tail (longest-processing-time-first).
+static int apply_slot_order(ratilqr_ctx* ctx, const std::vector<int32_t>& key, int P, int K) {
+  static const bool ascending = [] { const char* e = getenv("RATILQR_FLEET_ORDER"); return e && e[0] == 'a'; }();  // A/B runs
   const size_t B = (size_t)P * K;
-  std::vector<int32_t> iters(B), perm(B);
-  CU(cudaMemcpyAsync(iters.data(), ctx->sp.iters, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  std::vector<int32_t> key(P), order(P);
-  for (int p = 0; p < P; ++p) { int32_t mx = 0; for (int j = 0; j < K; ++j) mx = std::max(mx, iters[(size_t)p * K + j]); key[p] = mx; }
+  std::vector<int32_t> order(P), perm(B);
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  if (ascending) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  else std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] > key[b]; });
   for (int r = 0; r < P; ++r) for (int j = 0; j < K; ++j) perm[(size_t)r * K + j] = (int32_t)((size_t)order[r] * K + j);
   CU(ctx->d_perm.reserve(B * 4));
   CU(cudaMemcpyAsync(ctx->d_perm.p, perm.data(), B * 4, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));  // perm is a stack vector
   ctx->sp.perm = ctx->d_perm.as<int32_t>();
   return 0;
+}
+
+// key[p] = max iterations over the K instances of problem p in the launch that just finished.  Iteration counts are
+// a property of the problem far more than of theta (round-to-round correlation 0.95 on the C5 fleet), so the key also
+// predicts the next round -- and, kept in the context, the first round of the next MPC step of the same fleet.
+static int resort_slots_by_last_iters(ratilqr_ctx* ctx, int P, int K) {
+  const size_t B = (size_t)P * K;
+  std::vector<int32_t> iters(B);
+  CU(cudaMemcpyAsync(iters.data(), ctx->sp.iters, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t>& key = ctx->fleet_key;
+  key.assign(P, 0);
+  for (int p = 0; p < P; ++p) { int32_t mx = 0; for (int j = 0; j < K; ++j) mx = std::max(mx, iters[(size_t)p * K + j]); key[p] = mx; }
+  return apply_slot_order(ctx, key, P, K);
 }
 
 static int fetch_internal(ratilqr_ctx* ctx, ratilqr_ileqg_out* out) {
@@ -397,7 +465,10 @@ int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
   for (DBuf* b : all) b->release();
   for (DBuf& b : ctx->s) b.release();
   for (DBuf& b : ctx->d_mix) b.release();
+  ctx->d_order.release(); ctx->d_key.release();
+  if (ctx->h_key) cudaFreeHost(ctx->h_key);
   for (rlu::Module* um : ctx->user_models) { rlu::unload(*um); delete um; }
+  for (ratilqr_ctx* ch : ctx->children) ratilqr_destroy(ch);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -510,7 +581,9 @@ int32_t ratilqr_ce_costs(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, con
   if ((rc = check_launch(ctx, "k_ce_cost"))) return rc;
   CU(cudaMemcpyAsync(cost, ctx->d_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CU(cudaMemcpyAsync(status, ctx->sp.status, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = work_profile_enqueue(ctx, in->P, in->K))) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
+  work_profile_commit(ctx);
   return 0;
 }
 
@@ -845,12 +918,12 @@ int32_t ratilqr_pets_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, c
 }
 
 // ---- RAT iLQR for a fleet of problems (cross_entropy_bilevel_optimization.jl:364-415) ------------------------
-int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
-                               const ratilqr_ce_opts* ce, int32_t P, const double* x0, int32_t x0_count,
-                               const double* u_init, int32_t u_count, double kl_bound, const double* z_inject,
-                               int64_t nz, uint64_t seed, double* mu_init, double* sigma_init, double* theta_opt,
-                               double* value, double* theta_min, double* theta_max, double* mu, double* sigma,
-                               int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out) {
+static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                                const ratilqr_ce_opts* ce, int32_t P, long long p0, const double* x0, int32_t x0_count,
+                                const double* u_init, int32_t u_count, double kl_bound, const double* z_inject,
+                                int64_t nz, uint64_t seed, double* mu_init, double* sigma_init, double* theta_opt,
+                                double* value, double* theta_min, double* theta_max, double* mu, double* sigma,
+                                int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out) {
   if (!ctx) return -1;
   if (!ce || P < 1 || !mu_init || !sigma_init || !theta_opt || !value) FAIL(-1, "bad arguments");
   if (!(kl_bound >= 0)) FAIL(-3, "KL Divergence Bound must be non-negative");  // :368
@@ -861,7 +934,7 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   rll::CeFleet c;
   memset(&c, 0, sizeof(c));
   c.P = P; c.S = S; c.num_elite = ce->num_elite; c.iter_max = ce->iter_max; c.use_theta_max = ce->use_theta_max;
-  c.lambda = ce->lambda; c.kl = kl_bound; c.nz = nz; c.seed = seed;
+  c.lambda = ce->lambda; c.kl = kl_bound; c.nz = nz; c.seed = seed; c.p0 = p0;
   ratilqr_batch_in in;
   in.P = P; in.K = S; in.x0 = x0; in.x0_count = x0_count; in.u_init = u_init; in.u_count = u_count; in.theta = nullptr;
   int rc = 0, rounds = 0;
@@ -899,6 +972,9 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   if (kl_bound > 0) {
     c.theta = ctx->d_theta.as<double>(); c.value = ctx->sp.value; c.status = ctx->sp.status;
     ctx->sp.active = c.active;
+    if (sort_fleet && !ctx->coop && P >= 64 && (int)ctx->fleet_key.size() == P) {  // previous call on a fleet of this size
+      if ((rc = apply_slot_order(ctx, ctx->fleet_key, P, S))) return rc;
+    }
     while (true) {  // one round = draw -> batched solve -> per-problem CE logic; one host sync per round
       rll::launch_ce_draw(c, st);
       if ((rc = check_launch(ctx, "k_ce_draw"))) return rc;
@@ -910,19 +986,16 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
       CU(cudaMemcpyAsync(&n_active, c.n_active, 4, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       rounds++;
-      if (n_active == 0) break;
+      if (n_active == 0) {  // keep the work profile of the last round for the final solve and for the next MPC step
+        if (sort_fleet && !ctx->coop && P >= 64) { if ((rc = resort_slots_by_last_iters(ctx, P, S))) return rc; }
+        break;
+      }
       if (rounds > 100000) FAIL(-6, "CE redraw loop does not terminate (the reference would spin forever here)");
       if (sort_fleet && !ctx->coop && P >= 64) { if ((rc = resort_slots_by_last_iters(ctx, P, S))) return rc; }
     }
   }
-  std::vector<int32_t> last_key;
-  if (kl_bound > 0 && sort_fleet && !ctx->coop && P >= 64) {  // per-problem work of the last round orders the final solve too
-    std::vector<int32_t> it((size_t)P * S);
-    CU(cudaMemcpyAsync(it.data(), ctx->sp.iters, it.size() * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    last_key.resize(P);
-    for (int p = 0; p < P; ++p) { int32_t mx = 0; for (int j = 0; j < S; ++j) mx = std::max(mx, it[(size_t)p * S + j]); last_key[p] = mx; }
-  }
+  // (the per-problem work of the last round, ctx->fleet_key, orders the final solve too)
+  const bool order_final = kl_bound > 0 && sort_fleet && !ctx->coop && P >= 64 && (int)ctx->fleet_key.size() == P;
   // final solve at theta_opt with the retry rule (:390-414); B = P instances, theta on the device
   in.K = 1;
   const int fwant = final_out ? ((final_out->x ? 1 : 0) | (final_out->l ? 2 : 0) | (final_out->L ? 4 : 0)) : 0;
@@ -930,15 +1003,7 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   rll::launch_ce_pick_theta(c, ctx->d_theta.as<double>(), st);
   if ((rc = check_launch(ctx, "k_ce_pick_theta"))) return rc;
   ctx->sp.active = c.active;
-  if (!last_key.empty() && !ctx->coop) {
-    std::vector<int32_t> order(P);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return last_key[a] < last_key[b]; });
-    CU(ctx->d_perm.reserve((size_t)P * 4));
-    CU(cudaMemcpyAsync(ctx->d_perm.p, order.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
-    ctx->sp.perm = ctx->d_perm.as<int32_t>();
-  }
+  if (order_final) { if ((rc = apply_slot_order(ctx, ctx->fleet_key, P, 1))) return rc; }
   int final_rounds = 0;
   while (true) {
     if ((rc = run_internal(ctx, 1, nullptr))) return rc;
@@ -966,6 +1031,86 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   if (rounds_out) *rounds_out = rounds;
   for (int p = 0; p < P; ++p) if (err[p] == 1) FAIL(-5, "a problem exhausted its injected normal stream (or needed > 1e6 draws)");
   if (final_out) return fetch_internal(ctx, final_out);
+  return 0;
+}
+
+// Problems are independent, but each one's CE loop is a chain of sequential rounds, and a round of P * num_samples
+// instances that does not fill the GPU several times over ends in a long under-occupied tail (one thread per instance:
+// the slowest lanes finish alone).  So a large fleet is cut into contiguous blocks that run the SAME per-problem
+// algorithm concurrently, each on its own stream with its own workspace and host thread: while one block drains its
+// round, the others keep the SMs busy.  Results are identical to the one-block run (per-problem state, Philox streams
+// indexed by the global problem number).  RATILQR_FLEET_SPLIT=<k> overrides the block count (1 = off).
+static int fleet_blocks(const ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, int P, int S) {
+  if (const char* e = getenv("RATILQR_FLEET_SPLIT")) { int k = atoi(e); return k < 1 ? 1 : (k > 8 ? 8 : k); }
+  if (desc && desc->n > 6) return 1;                   // warp-cooperative kernel: already latency-oriented
+  if ((long long)P * S < 56832) return 1;              // less than one resident wave (148 SMs x 384) in total
+  (void)ctx;
+  return 3;  // A/B on the C5 fleet (profiles/r01_fleet_split_order_ab.jsonl): 1: 281 ms, 2: 279, 3: 268, 4: 277, 6+: worse
+}
+
+int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                               const ratilqr_ce_opts* ce, int32_t P, const double* x0, int32_t x0_count,
+                               const double* u_init, int32_t u_count, double kl_bound, const double* z_inject,
+                               int64_t nz, uint64_t seed, double* mu_init, double* sigma_init, double* theta_opt,
+                               double* value, double* theta_min, double* theta_max, double* mu, double* sigma,
+                               int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out) {
+  if (!ctx) return -1;
+  const int K = (ce && desc && P > 1) ? std::min(fleet_blocks(ctx, desc, P, ce->num_samples), (int)P) : 1;
+  if (K <= 1)
+    return ce_solve_fleet_block(ctx, desc, opts, ce, P, 0, x0, x0_count, u_init, u_count, kl_bound, z_inject, nz, seed, mu_init,
+                                sigma_init, theta_opt, value, theta_min, theta_max, mu, sigma, nz_used, rounds_out, final_out);
+  if (desc->cost_params_count != 1 && desc->cost_params_count != P) FAIL(-1, "cost_params_count must be 1 or P");
+  while ((int)ctx->children.size() < K - 1) {
+    ratilqr_ctx* ch = nullptr;
+    if (int rc = ratilqr_create(&ch, ctx->device)) FAIL(rc, "could not create a sub-fleet context");
+    ch->parent = ctx;
+    ctx->children.push_back(ch);
+  }
+  const size_t n = desc->n, m = desc->m, N = desc->N;
+  std::vector<int> rcs(K, 0), rounds(K, 0);
+  std::vector<std::thread> th;
+  auto run_block = [&](int b) {
+    const long long lo = (long long)P * b / K, hi = (long long)P * (b + 1) / K;
+    const int Pb = (int)(hi - lo);
+    ratilqr_ctx* c = b == 0 ? ctx : ctx->children[b - 1];
+    ratilqr_problem_desc d = *desc;
+    if (desc->cost_params_count == P) { d.cost_params = desc->cost_params + (size_t)lo * desc->n_cost_params; d.cost_params_count = Pb; }
+    ratilqr_ileqg_out fo;
+    if (final_out) {
+      fo = *final_out;
+      const size_t cap = (size_t)final_out->eps_hist_cap;
+      if (fo.x) fo.x += n * (N + 1) * lo;
+      if (fo.l) fo.l += m * N * lo;
+      if (fo.L) fo.L += m * n * N * lo;
+      if (fo.value) fo.value += lo;
+      if (fo.status) fo.status += lo;
+      if (fo.iters) fo.iters += lo;
+      if (fo.trials) fo.trials += lo;
+      if (fo.restarts) fo.restarts += lo;
+      if (fo.mu) fo.mu += lo;
+      if (fo.d_current) fo.d_current += lo;
+      if (fo.eps_hist) fo.eps_hist += 2 * cap * lo;
+    }
+    auto off = [&](double* q) { return q ? q + lo : nullptr; };
+    rcs[b] = ce_solve_fleet_block(c, &d, opts, ce, Pb, lo, x0_count == P ? x0 + n * lo : x0, x0_count == P ? Pb : x0_count,
+                                  u_count == P ? u_init + m * N * lo : u_init, u_count == P ? Pb : u_count, kl_bound,
+                                  z_inject ? z_inject + (size_t)lo * nz : nullptr, nz, seed, mu_init + lo, sigma_init + lo,
+                                  theta_opt + lo, value + lo, off(theta_min), off(theta_max), off(mu), off(sigma),
+                                  nz_used ? nz_used + lo : nullptr, &rounds[b], final_out ? &fo : nullptr);
+  };
+  if (!ce || !mu_init || !sigma_init || !theta_opt || !value) FAIL(-1, "bad arguments");
+  if ((x0_count != 1 && x0_count != P) || (u_count != 1 && u_count != P)) FAIL(-1, "x0_count/u_count must be 1 or P");
+  for (int b = 1; b < K; ++b) th.emplace_back(run_block, b);
+  run_block(0);
+  for (auto& t : th) t.join();
+  int rmax = 0;
+  for (int b = 0; b < K; ++b) {
+    rmax = std::max(rmax, rounds[b]);
+    if (b > 0) ctx->launches += ctx->children[b - 1]->launches, ctx->children[b - 1]->launches = 0;
+  }
+  if (rounds_out) *rounds_out = rmax;
+  for (int b = 0; b < K; ++b)
+    if (rcs[b]) { if (b > 0) ctx->err = ctx->children[b - 1]->err; return rcs[b]; }
   return 0;
 }
 

@@ -216,7 +216,7 @@ __global__ void k_ce_draw(CeFleet c) {
     if ((c.z && cur >= c.nz) || ++guard > 1000000) { c.err[p] = 1; c.active[p] = 0; break; }
     double z0, z1;
     if (c.z) z0 = c.z[(size_t)p * c.nz + cur];
-    else rl::philox_normal2(c.seed, (uint64_t)p, (uint32_t)cur, (uint32_t)(cur >> 32), &z0, &z1);
+    else rl::philox_normal2(c.seed, (uint64_t)(c.p0 + p), (uint32_t)cur, (uint32_t)(cur >> 32), &z0, &z1);
     cur++;
     double t = mm + ss * z0;                                // rand(rng, Normal(mu, sigma))
     if (t > 0.0) c.theta[(size_t)p * c.S + cnt++] = t;

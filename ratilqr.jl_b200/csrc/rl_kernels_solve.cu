@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "rl_coop.cuh"
 #include "rl_kernels_model.cuh"
@@ -23,8 +24,10 @@ template <class D, class CT, int THREADS, int MINB>
 static void launch_shape(const SolveParams& P, cudaStream_t st) {
   int blocks = (P.B + THREADS - 1) / THREADS;
   const size_t smem = UseStage<D>::value ? (size_t)2 * RL_STAGE_NV * THREADS * sizeof(double) : 0;
+  static std::mutex cfg_mutex;  // sub-fleets launch from several host threads (ratilqr_ce_solve_fleet)
   static bool configured = false;
   static int resident = MINB, sms = 148;
+  std::lock_guard<std::mutex> cfg_lock(cfg_mutex);
   if (!configured) {
     configured = true;
     auto kfn = k_ileqg_solve<D, CT, THREADS, MINB>;
@@ -50,8 +53,7 @@ static void launch_shape(const SolveParams& P, cudaStream_t st) {
 // launch shape = (threads per CTA, min resident CTAs per SM => register cap).  The default was chosen from
 // the sweep recorded in profiles/; RATILQR_SOLVE_SHAPE=<idx> overrides it for tuning runs.
 static int shape_override() {
-  static int v = -2;
-  if (v == -2) { const char* e = getenv("RATILQR_SOLVE_SHAPE"); v = e ? atoi(e) : -1; }
+  static const int v = [] { const char* e = getenv("RATILQR_SOLVE_SHAPE"); return e ? atoi(e) : -1; }();  // thread-safe init
   return v;
 }
 
@@ -192,12 +194,15 @@ void launch_gather(int n, int m, int N, int B, const double* X, const double* U,
 }
 
 // ---- theta sort: one CTA per problem, bitonic sort of (theta, index) in shared memory ---------------
-// perm[p*K + r] = p*K + (index of the r-th smallest theta of problem p); ties broken by index (total order).
-__global__ void __launch_bounds__(1024) k_sort_theta(const double* __restrict__ theta, int K, int Kpad, int32_t* __restrict__ perm) {
+// perm[r*K + j] = p*K + (index of the j-th smallest theta of problem p); ties broken by index (total order).
+// p = order[r] when a problem order is given (heaviest problems first, see rl_capi.cu), else p = r.
+__global__ void __launch_bounds__(1024) k_sort_theta(const double* __restrict__ theta, int K, int Kpad,
+                                                     const int32_t* __restrict__ order, int32_t* __restrict__ perm) {
   extern __shared__ unsigned char smem_raw[];
   double* key = reinterpret_cast<double*>(smem_raw);
   int32_t* idx = reinterpret_cast<int32_t*>(key + Kpad);
-  const size_t base = (size_t)blockIdx.x * K;
+  const size_t base = (size_t)(order ? order[blockIdx.x] : (int)blockIdx.x) * K;
+  const size_t slot0 = (size_t)blockIdx.x * K;
   for (int i = threadIdx.x; i < Kpad; i += blockDim.x) {
     double t = i < K ? theta[base + i] : HUGE_VAL;
     key[i] = (t != t) ? HUGE_VAL : t;  // NaN sorts last
@@ -218,15 +223,39 @@ __global__ void __launch_bounds__(1024) k_sort_theta(const double* __restrict__ 
       }
       __syncthreads();
     }
-  for (int i = threadIdx.x; i < K; i += blockDim.x) perm[base + i] = (int32_t)(base + idx[i]);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) perm[slot0 + i] = (int32_t)(base + idx[i]);
 }
 
-int launch_sort_theta(const double* theta, int P, int K, int32_t* perm, cudaStream_t st) {
-  if (K < 2 || K > 4096) return -1;  // nothing to gain / does not fit one CTA: caller keeps the identity
+// slots of problem rank r <- instances of problem order[r], in instance order (K = 1, or K too large for one CTA)
+__global__ void k_order_slots(const int32_t* __restrict__ order, int P, int K, int32_t* __restrict__ perm) {
+  size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= (size_t)P * K) return;
+  perm[s] = (int32_t)((size_t)order[s / K] * K + s % K);
+}
+
+// key[p] = max iterations over the K instances of problem p in the launch that just finished (slot-ordering profile)
+__global__ void k_problem_work(const int32_t* __restrict__ iters, int P, int K, int32_t* __restrict__ key) {
+  int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= P) return;
+  int mx = 0;
+  for (int j = lane; j < K; j += 32) mx = max(mx, iters[(size_t)p * K + j]);
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) key[p] = mx;
+}
+void launch_problem_work(const int32_t* iters, int P, int K, int32_t* key, cudaStream_t st) {
+  k_problem_work<<<(P + 3) / 4, 128, 0, st>>>(iters, P, K, key);
+}
+
+int launch_sort_theta(const double* theta, int P, int K, const int32_t* order, int32_t* perm, cudaStream_t st) {
+  if (K < 2 || K > 4096) {  // nothing to sort / does not fit one CTA: identity within the problem
+    if (!order) return -1;  // caller keeps the identity
+    k_order_slots<<<(unsigned)(((size_t)P * K + 255) / 256), 256, 0, st>>>(order, P, K, perm);
+    return 0;
+  }
   int Kpad = 2;
   while (Kpad < K) Kpad <<= 1;
   int threads = Kpad / 2 < 1024 ? (Kpad / 2 < 32 ? 32 : Kpad / 2) : 1024;
-  k_sort_theta<<<P, threads, (size_t)Kpad * 12, st>>>(theta, K, Kpad, perm);
+  k_sort_theta<<<P, threads, (size_t)Kpad * 12, st>>>(theta, K, Kpad, order, perm);
   return 0;
 }
 

@@ -21,8 +21,11 @@ int launch_solve_coop(int model_id, int cost_id, const rl::SolveParams& P, doubl
 void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg, const int32_t* cur,
                    const int32_t* perm, double* x_out, double* l_out, double* L_out, cudaStream_t st);
 
-// per-problem ascending sort of theta -> slot-to-instance permutation; returns -1 when not applicable
-int launch_sort_theta(const double* theta, int P, int K, int32_t* perm, cudaStream_t st);
+// per-problem ascending sort of theta -> slot-to-instance permutation, problems laid out in `order` (device, P entries,
+// or null = natural order); returns -1 when not applicable (caller keeps the identity)
+int launch_sort_theta(const double* theta, int P, int K, const int32_t* order, int32_t* perm, cudaStream_t st);
+// key[p] = max iterations over the K instances of problem p (device -> device)
+void launch_problem_work(const int32_t* iters, int P, int K, int32_t* key, cudaStream_t st);
 
 int launch_rollout_open(const CompArgs& a, cudaStream_t st);
 int launch_rollout_closed(const CompArgs& a, cudaStream_t st);
@@ -59,6 +62,7 @@ struct CeFleet {
   int P, S, num_elite, iter_max, use_theta_max;
   double lambda, kl;
   const double* z; long long nz; unsigned long long seed;   // injected normals (P*nz) or Philox
+  long long p0;             // global index of this block's first problem (Philox stream = p0 + p): sub-fleets draw what the whole fleet would
   double *mu_init, *sigma_init, *mu, *sigma, *theta_min, *theta_max, *theta_opt, *value_out;
   long long* cursor; int32_t *iter, *active, *err;
   double* theta;            // P*S draws (device), consumed by the solve kernel
