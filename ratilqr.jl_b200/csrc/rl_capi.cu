@@ -1147,9 +1147,14 @@ int32_t ratilqr_nm_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   c.iter = ctx->s[9].as<int32_t>(); c.active = ctx->s[10].as<int32_t>(); c.evals = ctx->s[11].as<int32_t>();
   c.phase = ctx->s[12].as<int32_t>(); c.n_active = ctx->s[13].as<int32_t>();
   int rounds = 0;
+  // same work placement as the CE fleet: problems heaviest-first by the iterations they needed in the previous round /
+  // previous call (resort_slots_by_last_iters); thread-per-instance kernel only
+  const char* esf = getenv("RATILQR_FLEET_SORT");
+  const bool sort_fleet = !(esf && esf[0] == '0') && P >= 64;
   if (kl_bound > 0) {
     c.theta = ctx->d_theta.as<double>(); c.value = ctx->sp.value; c.status = ctx->sp.status;
     ctx->sp.active = c.active;
+    if (sort_fleet && !ctx->coop && (int)ctx->fleet_key.size() == P) { if ((rc = apply_slot_order(ctx, ctx->fleet_key, P, 6))) return rc; }
     while (true) {
       rll::launch_nm_candidates(c, st);
       if ((rc = check_launch(ctx, "k_nm_candidates"))) return rc;
@@ -1162,11 +1167,14 @@ int32_t ratilqr_nm_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
       CU(cudaStreamSynchronize(st));
       if (n_active == 0) break;
       if (++rounds > 100000) FAIL(-6, "Nelder-Mead vertex search does not terminate (the reference would spin forever here)");
+      // the first rounds establish the profile; afterwards the per-problem work is stable, re-sort every 4th round
+      if (sort_fleet && !ctx->coop && (rounds <= 2 || rounds % 4 == 0)) { if ((rc = resort_slots_by_last_iters(ctx, P, 6))) return rc; }
     }
   }
   in.K = 1;
   const int fwant = final_out ? ((final_out->x ? 1 : 0) | (final_out->l ? 2 : 0) | (final_out->L ? 4 : 0)) : 0;
   if ((rc = stage_internal(ctx, desc, opts, &in, 0, true, fwant))) return rc;
+  if (sort_fleet && !ctx->coop && (int)ctx->fleet_key.size() == P) { if ((rc = apply_slot_order(ctx, ctx->fleet_key, P, 1))) return rc; }
   rll::launch_nm_final(c, ctx->d_theta.as<double>(), nullptr, nullptr, 0, st);
   if ((rc = check_launch(ctx, "k_nm_final"))) return rc;
   if ((rc = run_internal(ctx, 1, nullptr))) return rc;

@@ -74,12 +74,15 @@ __global__ void k_linearize(CompArgs a) {
   if (st && a.status) atomicMax(&a.status[b], st);
 }
 
+#ifndef RL_MC_MINB
+#define RL_MC_MINB(n) 1
+#endif
 // ---- Monte Carlo closed-loop rollouts (ileqg.jl:94-109 + :115-124): thread = sample -------------
 // The policy (xbar, l, L) of a problem is read by every thread of the block through the
 // read-only path (same address across the warp => one broadcast transaction); the injected
 // noise row of a sample is a contiguous n*N block (each 32-byte sector fully used).
 template <class D, class CT>
-__global__ void __launch_bounds__(128) k_mc_rollout(McArgs a) {
+__global__ void __launch_bounds__(128, RL_MC_MINB(D::n)) k_mc_rollout(McArgs a) {
   constexpr int n = D::n, m = D::m;
   int p = blockIdx.y;
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,9 +150,14 @@ __device__ double block_reduce(double v, Op op, double neutral, double* sh) {
 struct OpAdd { __device__ double operator()(double a, double b) const { return a + b; } };
 struct OpMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
 
+// register cap of the PETS rollout kernel: small systems do not need 164 registers; 2-3 resident 256-thread CTAs per SM
+// hide the latency of the FP64 transcendental chains (sincos, log, sqrt of the dynamics and of Box-Muller)
+#ifndef RL_PETS_MINB
+#define RL_PETS_MINB(n) ((n) <= 4 ? 3 : 1)
+#endif
 // ---- PETS: compute_cost_serial (pets.jl:128-157): block = sequence, thread = particle -------------
 template <class D, class CT>
-__global__ void __launch_bounds__(256) k_pets_costs(PetsArgs a) {
+__global__ void __launch_bounds__(256, RL_PETS_MINB(D::n)) k_pets_costs(PetsArgs a) {
   constexpr int n = D::n, m = D::m;
   __shared__ double sh[33];
   int ii = blockIdx.x;
