@@ -6,7 +6,7 @@ libratilqr_b200.so (see _lib.py).  The same class is reused by the test-suite to
 CPU oracle (prefix ``oracle_``) so that one harness feeds both sides identical inputs.
 
 All arrays are Fortran-ordered (column-major, instance index slowest), i.e. exactly what the
-Julia shim passes (julia/RATiLQRB200.jl).
+Julia shim passes (julia/src/RATiLQRB200.jl).
 """
 import ctypes as C
 

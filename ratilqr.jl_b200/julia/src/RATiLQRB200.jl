@@ -15,9 +15,10 @@ using RATiLQR
 import RATiLQR: solve!, compute_cost, compute_cost_serial, compute_cost_worker
 using LinearAlgebra
 
-const LIB = get(ENV, "RATILQR_B200_LIB", joinpath(@__DIR__, "..", "csrc", "libratilqr_b200.so"))
+const LIB = get(ENV, "RATILQR_B200_LIB", joinpath(@__DIR__, "..", "..", "csrc", "libratilqr_b200.so"))
 
-export DeviceDynamics, QuadraticCost, PowerLawCost, ConstantCovariance, b200_context
+export DeviceDynamics, QuadraticCost, PowerLawCost, ConstantCovariance, b200_context,
+       UserDeviceDynamics, user_cost, register_user_model!
 
 # ---- registered callables (subtypes of Function so the reference structs accept them,
 #      optimal_control_problems.jl:68-71) -----------------------------------------------------------
@@ -58,7 +59,14 @@ function QuadraticCost(n, m; Q=zeros(n, n), R=zeros(m, m), Qf=zeros(n, n), xg=ze
     p = vcat([ws0, ws1, c0, c1, h0], xg, vec(Q), vec(R), vec(Pc), vec(Qf))
     QuadraticCost(n, m, p, StageCost(1, p, n, m), TerminalCost(1, p, n, m))
 end
+# c = sum(x.^p + u.^p), h = h0 (the reference's shipped test problem, test/ileqg_test.jl:152-153); params [p, h0]
+struct PowerLawCost
+    params::Vector{Float64}
+    c::Function; h::Function
+end
+PowerLawCost(p, h0; n=2, m=2) = (q = Float64[p, h0]; PowerLawCost(q, StageCost(2, q, n, m), TerminalCost(2, q, n, m)))
 function (c::StageCost)(k, x, u)
+    c.id == 2 && return sum(x .^ c.params[1]) + sum(u .^ c.params[1])
     n, m, p = c.n, c.m, c.params
     xg = p[6:5+n]; Q = reshape(p[6+n:5+n+n^2], n, n); o = 5 + n + n^2
     R = reshape(p[o+1:o+m^2], m, m); Pc = reshape(p[o+m^2+1:o+m^2+n*m], n, m)
@@ -66,6 +74,7 @@ function (c::StageCost)(k, x, u)
     (p[1] + p[2] * k) * (0.5 * dx' * Q * dx + 0.5 * u' * R * u + dx' * Pc * u) + p[3] + p[4] * k
 end
 function (h::TerminalCost)(x)
+    h.id == 2 && return h.params[2]
     n, m, p = h.n, h.m, h.params
     o = 5 + n + n^2 + m^2 + n * m
     Qf = reshape(p[o+1:o+n^2], n, n); dx = x - p[6:5+n]
