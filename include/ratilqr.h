@@ -305,6 +305,18 @@ typedef struct {
   const char* cost_src;     /* NULL -> registered cost base_cost_id */
   int32_t base_cost_id;
   int32_t n_cost_params;    /* user cost: length of cp */
+  /* Optional structure declarations (NULL = dense): one entry per matrix element, column-major,
+   * 0 = identically zero, 1 = identically one, 2 = general.  a_kind n*n (df/dx), b_kind n*m (df/du) for
+   * user dynamics; q_kind n*n (cxx and the terminal Hessian), r_kind m*m (cuu), p_kind m*n (cux) for a
+   * user cost.  The kernels then skip / simplify those terms at compile time exactly like the registered
+   * models do (bit-identical results when the declaration is true).  ratilqr_user_model_register
+   * checks every declaration against the dual-number derivatives at random points and refuses a
+   * model whose declared zero / one is violated there. */
+  const int8_t* a_kind;
+  const int8_t* b_kind;
+  const int8_t* q_kind;
+  const int8_t* r_kind;
+  const int8_t* p_kind;
 } ratilqr_user_model_desc;
 /* compile only (NVRTC; no GPU, no ctx): 0 ok, -1 bad description, -20 NVRTC not loadable,
  * -21 compilation failed.  The compiler log is copied to log (NUL-terminated, truncated). */

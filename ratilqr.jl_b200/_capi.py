@@ -106,7 +106,8 @@ def make_opts(**kw):
 class UserModelDesc(C.Structure):  # ratilqr_user_model_desc
     _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("dynamics_src", C.c_char_p), ("base_model_id", C.c_int32),
                 ("n_model_params", C.c_int32), ("cost_src", C.c_char_p), ("base_cost_id", C.c_int32),
-                ("n_cost_params", C.c_int32)]
+                ("n_cost_params", C.c_int32), ("a_kind", C.POINTER(C.c_int8)), ("b_kind", C.POINTER(C.c_int8)),
+                ("q_kind", C.POINTER(C.c_int8)), ("r_kind", C.POINTER(C.c_int8)), ("p_kind", C.POINTER(C.c_int8))]
 
 
 MODEL_USER_BASE, COST_USER = 1000, 100
@@ -200,23 +201,36 @@ class CApi:
 
     # -- user-extensible device models (NVRTC) ------------------------------------------------
     @staticmethod
-    def _um_desc(n, m, dynamics_src, base_model_id, n_model_params, cost_src, base_cost_id, n_cost_params):
+    def _um_desc(n, m, dynamics_src, base_model_id, n_model_params, cost_src, base_cost_id, n_cost_params, kinds):
         enc = lambda t: None if t is None else t.encode()
-        return UserModelDesc(int(n), int(m), enc(dynamics_src), int(base_model_id), int(n_model_params), enc(cost_src),
-                             int(base_cost_id), int(n_cost_params))
+        keep = []
+
+        def kp(name, rows, cols):  # (rows, cols) table of 0 / 1 / 2 -> column-major int8 buffer
+            k = kinds.get(name)
+            if k is None:
+                return None
+            a = np.asfortranarray(np.asarray(k, dtype=np.int8).reshape(rows, cols))
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_int8))
+        d = UserModelDesc(int(n), int(m), enc(dynamics_src), int(base_model_id), int(n_model_params), enc(cost_src),
+                          int(base_cost_id), int(n_cost_params), kp("a_kind", n, n), kp("b_kind", n, m), kp("q_kind", n, n),
+                          kp("r_kind", m, m), kp("p_kind", m, n))
+        return d, keep
 
     def user_model_check(self, n, m, dynamics_src=None, cost_src=None, base_model_id=0, base_cost_id=0,
-                         n_model_params=0, n_cost_params=0):
-        """compile only (no GPU needed) -> (status, compiler log)"""
-        d = self._um_desc(n, m, dynamics_src, base_model_id, n_model_params, cost_src, base_cost_id, n_cost_params)
+                         n_model_params=0, n_cost_params=0, **kinds):
+        """compile only (no GPU needed) -> (status, compiler log).  kinds: a_kind (n, n), b_kind (n, m), q_kind (n, n),
+        r_kind (m, m), p_kind (m, n) tables of 0 / 1 / 2 declaring the structure of the derivatives (default dense)."""
+        d, keep = self._um_desc(n, m, dynamics_src, base_model_id, n_model_params, cost_src, base_cost_id, n_cost_params, kinds)
         log = C.create_string_buffer(1 << 16)
         rc = self.f_um_check(C.byref(d), log, len(log))
         return rc, log.value.decode(errors="replace")
 
     def user_model_register(self, n, m, dynamics_src=None, cost_src=None, base_model_id=0, base_cost_id=0,
-                            n_model_params=0, n_cost_params=0):
-        """compile + load into this context -> model id to put into Spec.model_id"""
-        d = self._um_desc(n, m, dynamics_src, base_model_id, n_model_params, cost_src, base_cost_id, n_cost_params)
+                            n_model_params=0, n_cost_params=0, **kinds):
+        """compile + load into this context -> model id to put into Spec.model_id (kinds as in user_model_check; a
+        declaration that the dual-number derivatives contradict at the probe points is refused)"""
+        d, keep = self._um_desc(n, m, dynamics_src, base_model_id, n_model_params, cost_src, base_cost_id, n_cost_params, kinds)
         log = C.create_string_buffer(1 << 16)
         mid = C.c_int32(0)
         rc = self.f_um_register(self.ctx, C.byref(d), C.byref(mid), log, len(log))

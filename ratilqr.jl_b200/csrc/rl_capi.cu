@@ -331,7 +331,7 @@ static int run_internal(ratilqr_ctx* ctx, int reps, float* ms_total) {
     if (ctx->dynamic) CU(cudaMemsetAsync(ctx->sp.queue, 0, 4, ctx->stream));
     if (ctx->staged_user) {
       const rlu::Module* um = ctx->staged_user;
-      if (int rc = user_launch(ctx, um, rlu::K_SOLVE, RL_GRID(ctx->sp.B, 64), 1, 64, um->solve_smem, &ctx->sp, "k_ileqg_solve")) return rc;
+      if (int rc = user_launch(ctx, um, rlu::K_SOLVE, RL_GRID(ctx->sp.B, um->solve_threads), 1, um->solve_threads, um->solve_smem, &ctx->sp, "k_ileqg_solve")) return rc;
       continue;
     }
     if (rll::launch_solve(ctx->model_id, ctx->cost_id, ctx->sp, ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
@@ -494,7 +494,74 @@ static int user_spec_from(const ratilqr_user_model_desc* um, rlu::Spec& sp) {
     if (rlh::model_dims(sp.base_model_id, &n, &m, &np)) sp.n_model_params = np;
   }
   if (sp.cost_src.empty()) sp.n_cost_params = rlh::cost_param_count(sp.base_cost_id, sp.n, sp.m);
+  if (sp.n < 1 || sp.n > 16 || sp.m < 1 || sp.m > 4) return 0;  // rejected by rlu::compile with a message
+  const size_t n = sp.n, m = sp.m;
+  if (!sp.dynamics_src.empty()) {
+    if (um->a_kind) sp.a_kind.assign(um->a_kind, um->a_kind + n * n);
+    if (um->b_kind) sp.b_kind.assign(um->b_kind, um->b_kind + n * m);
+  }
+  if (!sp.cost_src.empty()) {
+    if (um->q_kind) sp.q_kind.assign(um->q_kind, um->q_kind + n * n);
+    if (um->r_kind) sp.r_kind.assign(um->r_kind, um->r_kind + m * m);
+    if (um->p_kind) sp.p_kind.assign(um->p_kind, um->p_kind + m * n);
+  }
   return 0;
+}
+
+// Checks the declared structure of a freshly loaded user model against its dual-number derivatives at a few generic
+// points (generic parameters too: a structural zero / one holds for every parameter value, so this can only reject
+// false declarations).  Points where the model leaves its domain are skipped.  Returns "" or what is wrong.
+static std::string verify_user_structure(ratilqr_ctx* ctx, const rlu::Module& mod) {
+  const rlu::Spec& sp = mod.spec;
+  if (!mod.differentiable) return "";
+  if (sp.a_kind.empty() && sp.b_kind.empty() && sp.q_kind.empty() && sp.r_kind.empty() && sp.p_kind.empty()) return "";
+  const int n = sp.n, m = sp.m, N = 1, B = 6;
+  uint64_t lcg = 0x9E3779B97F4A7C15ull;
+  auto rnd = [&]() { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; return (double)(lcg >> 11) * (1.0 / 9007199254740992.0); };
+  std::vector<double> mp(std::max(sp.n_model_params, 1)), cp(std::max(sp.n_cost_params, 1)), W((size_t)n * n, 0.0);
+  for (auto& v : mp) v = 0.3 + 0.6 * rnd();
+  for (auto& v : cp) v = 0.3 + 0.6 * rnd();
+  for (int i = 0; i < n; ++i) W[i + (size_t)i * n] = 1.0;
+  std::vector<double> x((size_t)n * (N + 1) * B), u((size_t)m * N * B);
+  for (auto& v : x) v = 0.2 + 1.3 * rnd();
+  for (auto& v : u) v = -1.0 + 2.0 * rnd();
+  ratilqr_problem_desc d;
+  memset(&d, 0, sizeof(d));
+  d.model_id = mod.id; d.cost_id = mod.cost_id; d.n = n; d.m = m; d.N = N;
+  d.model_params = mp.data(); d.n_model_params = sp.n_model_params;
+  d.cost_params = cp.data(); d.n_cost_params = sp.n_cost_params; d.cost_params_count = 1;
+  d.W = W.data(); d.W_time_varying = 0;
+  std::vector<double> q((size_t)(N + 1) * B), qv((size_t)n * (N + 1) * B), Q((size_t)n * n * (N + 1) * B), r((size_t)m * N * B),
+      R((size_t)m * m * N * B), Pm((size_t)m * n * N * B), A((size_t)n * n * N * B), Bm((size_t)n * m * N * B);
+  std::vector<int32_t> st(B, 0);
+  if (ratilqr_linearize_batch(ctx, &d, B, x.data(), u.data(), q.data(), qv.data(), Q.data(), r.data(), R.data(), Pm.data(),
+                              A.data(), Bm.data(), st.data()))
+    return "structure check could not run: " + ctx->err;
+  auto bad = [&](const char* name, const std::vector<signed char>& k, const double* M, int rows, int cols, size_t per_inst,
+                 size_t stage_off) -> std::string {
+    if (k.empty()) return "";
+    for (int b = 0; b < B; ++b) {
+      if (st[b]) continue;
+      const double* Mb = M + per_inst * b + stage_off;
+      for (int j = 0; j < cols; ++j)
+        for (int i = 0; i < rows; ++i) {
+          const int kind = k[(size_t)i + (size_t)j * rows];
+          const double v = Mb[(size_t)i + (size_t)j * rows];
+          if ((kind == 0 && v != 0.0) || (kind == 1 && v != 1.0))
+            return std::string(name) + "[" + std::to_string(i) + "," + std::to_string(j) + "] is declared " +
+                   (kind == 0 ? "zero" : "one") + " but evaluates to " + std::to_string(v);
+        }
+    }
+    return "";
+  };
+  std::string e;
+  if (!(e = bad("a_kind", sp.a_kind, A.data(), n, n, (size_t)n * n * N, 0)).empty()) return e;
+  if (!(e = bad("b_kind", sp.b_kind, Bm.data(), n, m, (size_t)n * m * N, 0)).empty()) return e;
+  if (!(e = bad("q_kind", sp.q_kind, Q.data(), n, n, (size_t)n * n * (N + 1), 0)).empty()) return e;
+  if (!(e = bad("q_kind (terminal cost)", sp.q_kind, Q.data(), n, n, (size_t)n * n * (N + 1), (size_t)n * n * N)).empty()) return e;
+  if (!(e = bad("r_kind", sp.r_kind, R.data(), m, m, (size_t)m * m * N, 0)).empty()) return e;
+  if (!(e = bad("p_kind", sp.p_kind, Pm.data(), m, n, (size_t)m * n * N, 0)).empty()) return e;
+  return "";
 }
 
 int32_t ratilqr_user_model_check(const ratilqr_user_model_desc* um, char* log, int64_t log_cap) {
@@ -526,6 +593,14 @@ int32_t ratilqr_user_model_register(ratilqr_ctx* ctx, const ratilqr_user_model_d
   std::string e;
   if ((rc = rlu::load(c, *mod, e))) { delete mod; FAIL(rc, "user model: " + e); }
   ctx->user_models.push_back(mod);
+  const std::string wrong = verify_user_structure(ctx, *mod);
+  if (!wrong.empty()) {
+    ctx->user_models.pop_back();
+    rlu::unload(*mod);
+    delete mod;
+    copy_log("declared structure is wrong: " + wrong, log, log_cap);
+    FAIL(-25, "user model: declared structure is wrong: " + wrong);
+  }
   *model_id_out = mod->id;
   return 0;
 }

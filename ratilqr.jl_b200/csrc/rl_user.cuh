@@ -130,8 +130,10 @@ RL_HD bool rl_finite(double v) { return v - v == 0.0; }  // false for NaN and +-
 
 // ---- adapters: a user snippet -> the Dyn / Cost interfaces of rl_core.cuh ------------------------------------------
 // Body: struct with  template <class T> void operator()(const double* p, const T* x, const T* u, T* xn) const
-template <int N_, int M_, class Body>
-struct UserDyn : DenseKinds {
+// Kinds: struct with  static constexpr bool structured;  static constexpr int a_kind(int i, int j), b_kind(int i, int j)
+// (DenseKinds, or the user's declared structure generated by rl_user_host.cu)
+template <int N_, int M_, class Body, class Kinds = DenseKinds>
+struct UserDyn : Kinds {
   static constexpr int n = N_, m = M_;
   RL_HD static bool f(const double* p, const double* x, const double* u, double* xn) {
     Body()(p, x, u, xn);
@@ -146,12 +148,14 @@ struct UserDyn : DenseKinds {
 
 // Fn: struct with  template <class T> T stage(const double* cp, int k, const T* x, const T* u) const
 //                  template <class T> T terminal(const double* cp, const T* x) const
-template <int n, int m, int NPAR_, class Fn>
-struct UserCost {
-  static constexpr int NPAR = NPAR_;
+struct DenseCostKinds {
   RL_HD static constexpr int q_kind(int, int) { return 2; }
   RL_HD static constexpr int r_kind(int, int) { return 2; }
   RL_HD static constexpr int p_kind(int, int) { return 2; }
+};
+template <int n, int m, int NPAR_, class Fn, class CKinds = DenseCostKinds>
+struct UserCost : CKinds {
+  static constexpr int NPAR = NPAR_;
   RL_HD static bool stage(const double* RL_RESTRICT cp, int k, const double* x, const double* u, bool der,
                           double& q, double* qv, double* Q, double* r, double* R, double* P) {
     if (!der) {

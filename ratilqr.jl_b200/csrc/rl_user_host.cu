@@ -90,9 +90,17 @@ std::string cu_err(DriverApi* d, CUresult r) {
   return s ? s : "unknown driver error";
 }
 
-const char* kernel_expr(Kernel k) {
+// launch shape of the user solve kernel: 64 threads x 4 CTAs/SM (every register available).  The shape tuned for the
+// registered unicycle (128 x 3 = 168 registers) was within +-3 % on user pairs (+7 % only with both snippets structured),
+// so it stays an override for tuning: RATILQR_USER_SHAPE=128.
+static int solve_threads_for(const Spec&) {
+  if (const char* e = getenv("RATILQR_USER_SHAPE")) return atoi(e) == 128 ? 128 : 64;
+  return 64;
+}
+
+const char* kernel_expr(Kernel k, int solve_threads = 64) {
   switch (k) {
-    case K_SOLVE: return "rll::k_ileqg_solve<RluD, RluC, 64, 4>";
+    case K_SOLVE: return solve_threads == 128 ? "rll::k_ileqg_solve<RluD, RluC, 128, 3>" : "rll::k_ileqg_solve<RluD, RluC, 64, 4>";
     case K_ROLLOUT_OPEN: return "rll::k_rollout_open<RluD>";
     case K_ROLLOUT_CLOSED: return "rll::k_rollout_closed<RluD, RluC>";
     case K_INTEGRATE_COST: return "rll::k_integrate_cost<RluD, RluC>";
@@ -107,6 +115,22 @@ bool differentiable_cost(const Spec& s) { return !s.cost_src.empty() || s.base_c
 
 }  // namespace
 
+// "(i == 0 && j == 2) ? 2 : (...) ? 1 : <most common value>" for a rows x cols column-major table of kinds
+static std::string kind_expr(const std::vector<signed char>& k, int rows, int cols) {
+  int cnt[3] = {0, 0, 0};
+  for (signed char v : k) cnt[v < 0 ? 0 : (v > 2 ? 2 : v)]++;
+  int dflt = 0;
+  for (int v = 1; v < 3; ++v) if (cnt[v] > cnt[dflt]) dflt = v;
+  std::string e;
+  for (int j = 0; j < cols; ++j)
+    for (int i = 0; i < rows; ++i) {
+      int v = k[(size_t)i + (size_t)j * rows];
+      v = v < 0 ? 0 : (v > 2 ? 2 : v);
+      if (v != dflt) e += "(i == " + std::to_string(i) + " && j == " + std::to_string(j) + ") ? " + std::to_string(v) + " : ";
+    }
+  return e + std::to_string(dflt);
+}
+
 std::string make_source(const Spec& s) {
   std::string t;
   t += "#include \"rl_user.cuh\"\n#include \"rl_kernels_model.cuh\"\nusing rl::square;\n";
@@ -115,7 +139,15 @@ std::string make_source(const Spec& s) {
     t += "namespace ratilqr_user_dynamics {\n#line 1 \"dynamics\"\n" + s.dynamics_src + "\n}\n";
     t += "struct RluBody { template <class T> __device__ void operator()(const double* p, const T* x, const T* u, T* xn) const "
          "{ ratilqr_user_dynamics::dynamics<T>(p, x, u, xn); } };\n";
-    t += "typedef rl::UserDyn<" + N + ", " + M + ", RluBody> RluD;\n";
+    if (!s.a_kind.empty() || !s.b_kind.empty()) {
+      const std::vector<signed char> dense_a((size_t)s.n * s.n, 2), dense_b((size_t)s.n * s.m, 2);
+      t += "struct RluKinds {\n  static constexpr bool structured = true;\n"
+           "  RL_HD static constexpr int a_kind(int i, int j) { return " + kind_expr(s.a_kind.empty() ? dense_a : s.a_kind, s.n, s.n) + "; }\n"
+           "  RL_HD static constexpr int b_kind(int i, int j) { return " + kind_expr(s.b_kind.empty() ? dense_b : s.b_kind, s.n, s.m) + "; }\n};\n";
+      t += "typedef rl::UserDyn<" + N + ", " + M + ", RluBody, RluKinds> RluD;\n";
+    } else {
+      t += "typedef rl::UserDyn<" + N + ", " + M + ", RluBody> RluD;\n";
+    }
   } else {
     t += "typedef rl::Dyn<" + std::to_string(s.base_model_id) + "> RluD;\n";
     t += "static_assert(RluD::n == " + N + " && RluD::m == " + M + ", \"n/m do not match the registered model\");\n";
@@ -126,7 +158,16 @@ std::string make_source(const Spec& s) {
          "  template <class T> __device__ T stage(const double* cp, int k, const T* x, const T* u) const { return ratilqr_user_cost::stage_cost<T>(cp, k, x, u); }\n"
          "  template <class T> __device__ T terminal(const double* cp, const T* x) const { return ratilqr_user_cost::terminal_cost<T>(cp, x); }\n"
          "};\n";
-    t += "typedef rl::UserCost<" + N + ", " + M + ", " + std::to_string(s.n_cost_params) + ", RluCostFn> RluC;\n";
+    if (!s.q_kind.empty() || !s.r_kind.empty() || !s.p_kind.empty()) {
+      const std::vector<signed char> dq((size_t)s.n * s.n, 2), dr((size_t)s.m * s.m, 2), dp((size_t)s.m * s.n, 2);
+      t += "struct RluCostKinds {\n"
+           "  RL_HD static constexpr int q_kind(int i, int j) { return " + kind_expr(s.q_kind.empty() ? dq : s.q_kind, s.n, s.n) + "; }\n"
+           "  RL_HD static constexpr int r_kind(int i, int j) { return " + kind_expr(s.r_kind.empty() ? dr : s.r_kind, s.m, s.m) + "; }\n"
+           "  RL_HD static constexpr int p_kind(int i, int j) { return " + kind_expr(s.p_kind.empty() ? dp : s.p_kind, s.m, s.n) + "; }\n};\n";
+      t += "typedef rl::UserCost<" + N + ", " + M + ", " + std::to_string(s.n_cost_params) + ", RluCostFn, RluCostKinds> RluC;\n";
+    } else {
+      t += "typedef rl::UserCost<" + N + ", " + M + ", " + std::to_string(s.n_cost_params) + ", RluCostFn> RluC;\n";
+    }
   } else {
     t += "typedef rl::Cost<" + std::to_string(s.base_cost_id) + ", " + N + ", " + M + "> RluC;\n";
   }
@@ -144,6 +185,10 @@ int compile(const Spec& s, Compiled& out) {
   }
   if (s.cost_src.empty() && rlh::cost_param_count(s.base_cost_id, s.n, s.m) < 0) { out.log = "base_cost_id is not a registered cost"; return -1; }
   if (!s.cost_src.empty() && s.n_cost_params < 0) { out.log = "n_cost_params must be >= 0"; return -1; }
+  for (const auto* k : {&s.q_kind, &s.r_kind, &s.p_kind})
+    for (signed char v : *k) if (v != 0 && v != 2) { out.log = "q_kind / r_kind / p_kind entries must be 0 or 2"; return -1; }
+  for (const auto* k : {&s.a_kind, &s.b_kind})
+    for (signed char v : *k) if (v < 0 || v > 2) { out.log = "a_kind / b_kind entries must be 0, 1 or 2"; return -1; }
   NvrtcApi* nv = nvrtc_api();
   if (!nv) { out.log = "libnvrtc.so.12 could not be loaded (set CUDA_HOME or LD_LIBRARY_PATH)"; return -20; }
   const std::string src = make_source(s);
@@ -153,7 +198,7 @@ int compile(const Spec& s, Compiled& out) {
   const bool diff = differentiable_cost(s);
   for (int k = 0; k < K_COUNT; ++k) {
     if (!diff && (k == K_SOLVE || k == K_LINEARIZE)) continue;
-    nv->AddNameExpression(prog, kernel_expr((Kernel)k));
+    nv->AddNameExpression(prog, kernel_expr((Kernel)k, solve_threads_for(s)));
   }
   // same code generation rules as the library build (csrc/Makefile): explicit fma only
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-default-device", "-lineinfo"};
@@ -169,7 +214,7 @@ int compile(const Spec& s, Compiled& out) {
   for (int k = 0; k < K_COUNT; ++k) {
     if (!diff && (k == K_SOLVE || k == K_LINEARIZE)) continue;
     const char* low = nullptr;
-    if (nv->GetLoweredName(prog, kernel_expr((Kernel)k), &low) == NVRTC_SUCCESS && low) out.lowered[k] = low;
+    if (nv->GetLoweredName(prog, kernel_expr((Kernel)k, solve_threads_for(s)), &low) == NVRTC_SUCCESS && low) out.lowered[k] = low;
   }
   size_t csz = 0;
   nv->GetCUBINSize(prog, &csz);
@@ -197,9 +242,11 @@ int load(const Compiled& c, Module& m, std::string& err) {
   }
   // thread-private cp.async staging area of the solve kernel (rl::UseStage / rl::RL_STAGE_NV), 64-thread CTAs
   const int nv = m.spec.n + 2 * m.spec.m + m.spec.m * m.spec.n;
-  m.solve_smem = (nv <= 16) ? (size_t)2 * 16 * 64 * sizeof(double) : 0;
+  m.solve_threads = solve_threads_for(m.spec);
+  const int minb = m.solve_threads == 128 ? 3 : 4;
+  m.solve_smem = (nv <= 16) ? (size_t)2 * 16 * m.solve_threads * sizeof(double) : 0;
   if (m.fn[K_SOLVE] && m.solve_smem) {
-    int pct = (int)((4 * (m.solve_smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 5;
+    int pct = (int)((minb * (m.solve_smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 5;
     d->FuncSetAttribute((CUfunction)m.fn[K_SOLVE], CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct > 100 ? 100 : pct);
   }
   return 0;

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 namespace rlu {
 
@@ -16,6 +17,9 @@ struct Spec {
   int n = 0, m = 0, n_model_params = 0, n_cost_params = 0;
   int base_model_id = 0, base_cost_id = 0;  // used when the corresponding snippet is empty
   std::string dynamics_src, cost_src;
+  // declared structure (empty = dense): 0 zero, 1 one, 2 general; column-major.  a n*n, b n*m (dynamics snippet);
+  // q n*n, r m*m, p m*n (cost snippet)
+  std::vector<signed char> a_kind, b_kind, q_kind, r_kind, p_kind;
 };
 
 struct Compiled {
@@ -31,6 +35,7 @@ struct Module {
   void* cu_module = nullptr;
   void* fn[K_COUNT] = {};
   size_t solve_smem = 0;
+  int solve_threads = 64;  // launch shape of the solve kernel (threads per CTA; the register cap follows from min CTAs/SM)
 };
 
 // the translation unit handed to NVRTC (exposed for diagnostics / tests)

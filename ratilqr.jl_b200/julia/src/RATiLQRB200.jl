@@ -132,6 +132,7 @@ user_cost(n, m, params, src, c_cpu, h_cpu) = (UserStageCost(Int32(100), Float64.
 struct UserModelDesc
     n::Int32; m::Int32; dynamics_src::Cstring; base_model_id::Int32; n_model_params::Int32
     cost_src::Cstring; base_cost_id::Int32; n_cost_params::Int32
+    a_kind::Ptr{Int8}; b_kind::Ptr{Int8}; q_kind::Ptr{Int8}; r_kind::Ptr{Int8}; p_kind::Ptr{Int8}   # optional structure, C_NULL = dense
 end
 dims_of(f::DeviceDynamics) = MODEL_DIMS[f.model_id]
 dims_of(f::UserDeviceDynamics) = (f.n, f.m)
@@ -147,7 +148,7 @@ function register_user_model!(f, c)
     GC.@preserve dsrc csrc log begin
         um = UserModelDesc(n, m, ud ? Base.unsafe_convert(Cstring, dsrc) : Cstring(C_NULL), ud ? 0 : f.model_id,
                            length(f.params), uc ? Base.unsafe_convert(Cstring, csrc) : Cstring(C_NULL), uc ? 0 : c.id,
-                           uc ? length(c.params) : 0)
+                           uc ? length(c.params) : 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
         rc = ccall((:ratilqr_user_model_register, LIB), Int32, (Ptr{Cvoid}, Ref{UserModelDesc}, Ref{Int32}, Ptr{UInt8}, Int64),
                    b200_context(), um, id, log, length(log))
         rc == 0 || error("ratilqr_user_model_register failed ($rc):\n" * unsafe_string(pointer(log)))

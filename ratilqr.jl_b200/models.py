@@ -273,8 +273,9 @@ class UserDynamics(DeviceDynamics):
     const T* u, T* xn)`  (include/ratilqr.h, "user-extensible device models").  `py` is an optional host callable
     `py(p, x, u) -> xn` so that the object is still callable on the CPU like a Julia closure; the solvers never use it."""
 
-    def __init__(self, n, m, src, params=(), py=None):
+    def __init__(self, n, m, src, params=(), py=None, a_kind=None, b_kind=None):
         self.model_id, self.n, self.m, self.src, self.py = None, int(n), int(m), src, py
+        self.a_kind, self.b_kind = a_kind, b_kind  # optional declared structure of df/dx (n, n), df/du (n, m): 0 / 1 / 2
         self.params = np.asarray(params, dtype=np.float64).reshape(-1)
         assert self.params.size <= 8, "user dynamics take at most 8 parameters"
 
@@ -302,9 +303,10 @@ class UserCost(DeviceCost):
 
     cost_id = 100  # RATILQR_COST_USER
 
-    def __init__(self, src, params=(), stage_py=None, terminal_py=None):
+    def __init__(self, src, params=(), stage_py=None, terminal_py=None, q_kind=None, r_kind=None, p_kind=None):
         super().__init__()
         self.src, self.stage_py, self.terminal_py = src, stage_py, terminal_py
+        self.q_kind, self.r_kind, self.p_kind = q_kind, r_kind, p_kind  # optional structure of cxx (n, n), cuu (m, m), cux (m, n): 0 / 2
         self._params = np.asarray(params, dtype=np.float64).reshape(-1)
 
     def stage(self, k, x, u):
@@ -334,9 +336,11 @@ def register_user_model(backend, dynamics, cost):
         dynamics_src=dynamics.src if ud else None, base_model_id=0 if ud else dynamics.model_id,
         n_model_params=dynamics.params.size,
         cost_src=cost.src if uc else None, base_cost_id=0 if uc else cost.cost_id,
-        n_cost_params=cost.params().size if uc else 0)
+        n_cost_params=cost.params().size if uc else 0,
+        a_kind=dynamics.a_kind if ud else None, b_kind=dynamics.b_kind if ud else None,
+        q_kind=cost.q_kind if uc else None, r_kind=cost.r_kind if uc else None, p_kind=cost.p_kind if uc else None)
     if ud:
-        bound = UserDynamics(dynamics.n, dynamics.m, dynamics.src, dynamics.params, dynamics.py)
+        bound = UserDynamics(dynamics.n, dynamics.m, dynamics.src, dynamics.params, dynamics.py, dynamics.a_kind, dynamics.b_kind)
     else:
         bound = DeviceDynamics(dynamics.model_id, dynamics.params)
         bound.host_model_id = dynamics.model_id

@@ -25,6 +25,12 @@ t0 = time.perf_counter()
 mid = be.user_model_register(4, 2, dynamics_src=snip("unicycle_dynamics"), n_model_params=1, base_cost_id=1)
 t_reg = time.perf_counter() - t0
 mid2 = be.user_model_register(4, 2, dynamics_src=snip("unicycle_dynamics"), n_model_params=1, cost_src=snip("goal_cost"), n_cost_params=11)
+UNI_A = np.array([[1, 0, 2, 2], [0, 1, 2, 2], [0, 0, 1, 0], [0, 0, 0, 1]])
+UNI_B = np.array([[0, 0], [0, 0], [0, 2], [2, 0]])
+mid3 = be.user_model_register(4, 2, dynamics_src=snip("unicycle_dynamics"), n_model_params=1, cost_src=snip("goal_cost"), n_cost_params=11,
+                              a_kind=UNI_A, b_kind=UNI_B, q_kind=2 * np.eye(4, dtype=int), r_kind=2 * np.eye(2, dtype=int),
+                              p_kind=np.zeros((2, 4), dtype=int))
+mid4 = be.user_model_register(4, 2, dynamics_src=snip("unicycle_dynamics"), n_model_params=1, base_cost_id=1, a_kind=UNI_A, b_kind=UNI_B)
 W = ref.W.reshape(4, 4, order="F")
 # goal_cost.inc parameters per problem: [Qdiag, Rdiag, xg, qf] from the registered quadratic blocks
 cp = ref.cost_params.reshape(P, -1)
@@ -35,7 +41,9 @@ gcp = np.concatenate([np.diagonal(Q, axis1=1, axis2=2), np.diagonal(Rm, axis1=1,
                       (Qf[:, 0, 0] / Q[:, 0, 0])[:, None]], axis=1)
 specs = {"registered unicycle + QuadraticCost (structure-specialised kernel)": ref,
          "user unicycle snippet + registered QuadraticCost": _capi.Spec(mid, 1, 4, 2, ref.N, ref.model_params, cp, W),
-         "user unicycle snippet + user goal-cost snippet (second-order duals)": _capi.Spec(mid2, _capi.COST_USER, 4, 2, ref.N, ref.model_params, gcp, W)}
+         "user unicycle snippet + user goal-cost snippet (second-order duals)": _capi.Spec(mid2, _capi.COST_USER, 4, 2, ref.N, ref.model_params, gcp, W),
+         "user unicycle snippet with declared structure + registered QuadraticCost": _capi.Spec(mid4, 1, 4, 2, ref.N, ref.model_params, cp, W),
+         "both snippets with declared structure (a/b/q/r/p kinds)": _capi.Spec(mid3, _capi.COST_USER, 4, 2, ref.N, ref.model_params, gcp, W)}
 base = None
 for name, spec in specs.items():
     be.stage(spec, x0, u, theta, P=P)

@@ -18,7 +18,8 @@ using namespace rl;
 // ---- statically compiled copies of the USER-MODEL snippets of tests/user_models/ ---------------------------------
 // The GPU tests hand the same text to NVRTC (ratilqr_user_model_register); here g++ compiles it through the same
 // adapters (rl_user.cuh: UserDyn / UserCost, forward-mode duals), so the user-model arithmetic has a CPU check too.
-// hostemu-only numbering: model 1000 = unicycle snippet, 1001 = drag car; cost 100 = goal cost, 101 = obstacle cost.
+// hostemu-only numbering: model 1000 = unicycle snippet, 1001 = drag car, 1002 = unicycle with declared structure;
+// cost 100 = goal cost, 101 = obstacle cost, 102 = goal cost with declared (diagonal) structure.
 using rl::square;
 namespace um_unicycle {
 #include "../user_models/unicycle_dynamics.inc"
@@ -42,19 +43,35 @@ struct UmObstacleFn {
   template <class T> T stage(const double* cp, int k, const T* x, const T* u) const { return um_obstacle::stage_cost<T>(cp, k, x, u); }
   template <class T> T terminal(const double* cp, const T* x) const { return um_obstacle::terminal_cost<T>(cp, x); }
 };
+// declared structure (what ratilqr_user_model_desc.a_kind ... p_kind generate): model 1002 / cost 102
+struct UmUnicycleKinds {
+  static constexpr bool structured = true;
+  static constexpr int a_kind(int i, int j) { return i == j ? 1 : ((i < 2 && j >= 2) ? 2 : 0); }
+  static constexpr int b_kind(int i, int j) { return ((i == 2 && j == 1) || (i == 3 && j == 0)) ? 2 : 0; }
+};
+struct UmDiagCostKinds {
+  static constexpr int q_kind(int i, int j) { return i == j ? 2 : 0; }
+  static constexpr int r_kind(int i, int j) { return i == j ? 2 : 0; }
+  static constexpr int p_kind(int, int) { return 0; }
+};
+typedef UserDyn<4, 2, UmUnicycleBody, UmUnicycleKinds> UmUnicycleS;
+typedef UserCost<4, 2, 11, UmGoalFn, UmDiagCostKinds> UmGoalS;
 typedef UserDyn<4, 2, UmUnicycleBody> UmUnicycle;
 typedef UserDyn<4, 2, UmDragCarBody> UmDragCar;
 typedef UserCost<4, 2, 11, UmGoalFn> UmGoal;
 typedef UserCost<4, 2, 15, UmObstacleFn> UmObstacle;
 
 static const char* hm_check_desc(const ratilqr_problem_desc* d, bool differentiable) {
-  if (d && d->model_id < 1000 && d->cost_id < 100) return rlh::check_desc(d, differentiable);
+  if (d && d->model_id < 1000 && d->cost_id < 100) return rlh::check_desc(d, differentiable);  // registered pair
   if (!d || d->n != 4 || d->m != 2 || d->N < 1 || !d->W || !d->cost_params) return "bad user-model description";
   return nullptr;
 }
 
 template <class F> static int dispatch(int model_id, int cost_id, F&& fn) {
-  if (model_id >= 1000 || cost_id == 100 || cost_id == 101) {  // (RL_COST_QUAD_DIAG is 0x101: not a user id)
+  if (model_id >= 1000 || cost_id == 100 || cost_id == 101 || cost_id == 102) {  // (RL_COST_QUAD_DIAG is 0x101: not a user id)
+    if (model_id == 1002 && cost_id == 102) { fn(UmUnicycleS(), UmGoalS()); return 0; }
+    if (model_id == 1002 && cost_id == 100) { fn(UmUnicycleS(), UmGoal()); return 0; }
+    if (model_id == 1000 && cost_id == 102) { fn(UmUnicycle(), UmGoalS()); return 0; }
     using Quad = Cost<RATILQR_COST_QUADRATIC, 4, 2>;
     if (model_id == 1000 && cost_id == RATILQR_COST_QUADRATIC) { fn(UmUnicycle(), Quad()); return 0; }
     if (model_id == 1000 && cost_id == 100) { fn(UmUnicycle(), UmGoal()); return 0; }

@@ -40,6 +40,12 @@ def snippet(name):
 
 # hostemu-only numbering of the statically compiled snippets (tests/_hostemu/hostemu.cpp)
 HM_UNICYCLE, HM_DRAGCAR, HM_GOAL, HM_OBSTACLE = 1000, 1001, 100, 101
+HM_UNICYCLE_STRUCT, HM_GOAL_STRUCT = 1002, 102  # the same snippets with declared structure
+
+# declared structure of the unicycle snippet and of the goal cost (include/ratilqr.h: a_kind ... p_kind)
+UNI_A = np.array([[1, 0, 2, 2], [0, 1, 2, 2], [0, 0, 1, 0], [0, 0, 0, 1]])
+UNI_B = np.array([[0, 0], [0, 0], [0, 2], [2, 0]])
+DIAG_Q, DIAG_R, ZERO_P = 2 * np.eye(4, dtype=int), 2 * np.eye(2, dtype=int), np.zeros((2, 4), dtype=int)
 
 QD, RD, XG, QF = np.array([1.0, 1.0, 0.1, 0.1]), np.array([0.1, 0.1]), np.array([5.0, 5.0, 0.0, 0.0]), 10.0
 GOAL_CP = np.concatenate([0.01 * QD, 0.01 * RD, XG, [QF]])                       # goal_cost.inc
@@ -154,6 +160,18 @@ def test_hostemu_user_goal_cost_matches_quadratic(hostemu_be, oracle_be, model_i
         assert relerr(g[k], o[k]) < RTOL, k
 
 
+@pytest.mark.parametrize("pair", [(HM_UNICYCLE_STRUCT, HM_GOAL_STRUCT), (HM_UNICYCLE_STRUCT, HM_GOAL), (HM_UNICYCLE, HM_GOAL_STRUCT)])
+def test_hostemu_declared_structure_is_bit_identical(hostemu_be, pair):
+    """skipping declared zeros / ones changes no finite result (fma(x, 0, acc) == acc): structured == dense, bit for bit"""
+    theta = wl.c2_thetas(24)
+    spec_d, x0, u, _ = c2_like(HM_UNICYCLE, HM_GOAL, GOAL_CP)
+    spec_s, _, _, _ = c2_like(pair[0], pair[1], GOAL_CP)
+    d = hostemu_be.ileqg_solve_batch(spec_d, x0, u, theta)
+    g = hostemu_be.ileqg_solve_batch(spec_s, x0, u, theta)
+    for k in ("status", "iters", "trials", "value", "x", "l", "L"):
+        assert np.array_equal(d[k], g[k]), k
+
+
 def test_hostemu_new_model_derivatives(hostemu_be):
     spec, _, _, _ = c2_like(HM_DRAGCAR, HM_OBSTACLE, OBST_CP, mp=DRAG_P, N=6)
     check_linearize_against_numpy(hostemu_be, spec, OBST_CP, DRAG_P)
@@ -204,6 +222,19 @@ def test_nvrtc_reports_snippet_errors(lib_api):
     assert rc == -1
     rc, log = lib_api.user_model_check(n=4, m=2, cost_src=snippet("goal_cost"), base_model_id=R.models.MODEL_CARTPOLE, n_cost_params=11)
     assert rc == -1 and "registered model" in log  # cart-pole is (4, 1)
+    rc, log = lib_api.user_model_check(n=4, m=2, dynamics_src=snippet("unicycle_dynamics"), n_model_params=1, base_cost_id=1,
+                                       a_kind=3 * np.ones((4, 4), int))
+    assert rc == -1 and "a_kind" in log
+    rc, log = lib_api.user_model_check(n=4, m=2, dynamics_src=snippet("unicycle_dynamics"), n_model_params=1,
+                                       cost_src=snippet("goal_cost"), n_cost_params=11, q_kind=np.ones((4, 4), int))
+    assert rc == -1 and "q_kind" in log
+
+
+def test_nvrtc_compiles_declared_structure(lib_api):
+    rc, log = _check(lib_api, n=4, m=2, dynamics_src=snippet("unicycle_dynamics"), n_model_params=1,
+                     cost_src=snippet("goal_cost"), n_cost_params=11, a_kind=UNI_A, b_kind=UNI_B, q_kind=DIAG_Q, r_kind=DIAG_R,
+                     p_kind=ZERO_P)
+    assert rc == 0, log
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -249,6 +280,33 @@ def test_gpu_user_goal_cost_vs_oracle(gpu_be, oracle_be, gpu_user, pair):
     cg = gpu_be.ce_costs(spec_u, x0, u, theta, 0.1)[0]
     co = oracle_be.ce_costs(ref, x0, u, theta, 0.1)[0]
     assert relerr(cg, co) < RTOL
+
+
+@pytest.mark.gpu
+def test_gpu_declared_structure(gpu_be, oracle_be, gpu_user):
+    """a true declaration: bit-identical to the dense registration and 1e-9 from the oracle; a false one is refused"""
+    mid = gpu_be.user_model_register(4, 2, dynamics_src=snippet("unicycle_dynamics"), n_model_params=1, cost_src=snippet("goal_cost"),
+                                     n_cost_params=11, a_kind=UNI_A, b_kind=UNI_B, q_kind=DIAG_Q, r_kind=DIAG_R, p_kind=ZERO_P)
+    theta = wl.c2_thetas(128)
+    spec_s, x0, u, ref = c2_like(mid, _capi.COST_USER, GOAL_CP)
+    spec_d, _, _, _ = c2_like(gpu_user["uni+goal"], _capi.COST_USER, GOAL_CP)
+    s = gpu_be.ileqg_solve_batch(spec_s, x0, u, theta)
+    d = gpu_be.ileqg_solve_batch(spec_d, x0, u, theta)
+    o = oracle_be.ileqg_solve_batch(ref, x0, u, theta)
+    for k in ("status", "iters", "trials", "value", "x", "l", "L"):
+        assert np.array_equal(s[k], d[k]), k
+    assert np.array_equal(s["iters"], o["iters"])
+    for k in ("value", "x", "l", "L"):
+        assert relerr(s[k], o[k]) < RTOL, k
+    wrong_a = UNI_A.copy()
+    wrong_a[0, 2] = 0  # d(px')/d(psi) = -dt v sin(psi) is not zero
+    with pytest.raises(_capi.ApiError, match=r"a_kind\[0,2\] is declared zero"):
+        gpu_be.user_model_register(4, 2, dynamics_src=snippet("unicycle_dynamics"), n_model_params=1, base_cost_id=1, a_kind=wrong_a)
+    wrong_p = DIAG_Q.copy()
+    wrong_p[1, 1] = 0  # cxx[1,1] = Q_11 is not zero
+    with pytest.raises(_capi.ApiError, match=r"q_kind"):
+        gpu_be.user_model_register(4, 2, base_model_id=R.models.MODEL_UNICYCLE, cost_src=snippet("goal_cost"), n_cost_params=11,
+                                   q_kind=wrong_p)
 
 
 @pytest.mark.gpu
