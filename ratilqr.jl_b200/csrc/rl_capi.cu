@@ -1175,8 +1175,13 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   };
   if (!ce || !mu_init || !sigma_init || !theta_opt || !value) FAIL(-1, "bad arguments");
   if ((x0_count != 1 && x0_count != P) || (u_count != 1 && u_count != P)) FAIL(-1, "x0_count/u_count must be 1 or P");
-  for (int b = 1; b < K; ++b) th.emplace_back(run_block, b);
+  int spawned = 1;
+  try {
+    for (int b = 1; b < K; ++b) { th.emplace_back(run_block, b); ++spawned; }
+  } catch (...) {  // no more host threads: the remaining blocks run on this one, after block 0
+  }
   run_block(0);
+  for (int b = spawned; b < K; ++b) run_block(b);
   for (auto& t : th) t.join();
   int rmax = 0;
   for (int b = 0; b < K; ++b) {
