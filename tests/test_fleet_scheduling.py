@@ -26,6 +26,11 @@ def test_profile_order_does_not_change_results(oracle_be):
         o = oracle_be.ileqg_solve_batch(spec, x0, u, th2, P=P)
         assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["iters"], o["iters"])
         assert np.max(np.abs(g["x"] - o["x"])) < 1e-9 * max(1.0, np.max(np.abs(o["x"])))
+        th1p = th1[:P]                                           # one theta per problem (K = 1): slots follow the problem order
+        g1 = be.ileqg_solve_batch(spec, x0, u, th1p, P=P)
+        o1 = oracle_be.ileqg_solve_batch(spec, x0, u, th1p, P=P)
+        assert np.array_equal(g1["status"], o1["status"]) and np.array_equal(g1["iters"], o1["iters"])
+        assert np.max(np.abs(g1["l"] - o1["l"])) < 1e-9 * max(1.0, np.max(np.abs(o1["l"])))
         ref = oracle_be.ce_costs(spec, x0, u, th2, 0.1, P=P)[0]
         fin = np.isfinite(ref)
         assert np.array_equal(fin, np.isfinite(warm[0]))
