@@ -246,11 +246,14 @@ def main():
     fprob, fcps, fx0, fu = wl.fleet(Pf, key=70 + rank)
     fspec = fprob.spec(cost_params=fcps)
     be.ce_solve_fleet(fspec, fx0, fu, 0.1, 1.0, 2.0, seed=7 + rank, want=())  # warm-up (allocations)
-    barrier()
-    t0 = time.perf_counter()
-    fr = be.ce_solve_fleet(fspec, fx0, fu, 0.1, 1.0, 2.0, seed=7 + rank, want=("l",))
-    barrier()
-    fleet_s = max_over_ranks(time.perf_counter() - t0)
+    fleet_all = []
+    for _ in range(3):  # latency-bound (six sequential solves per problem): report the best of three and all three
+        barrier()
+        t0 = time.perf_counter()
+        fr = be.ce_solve_fleet(fspec, fx0, fu, 0.1, 1.0, 2.0, seed=7 + rank, want=("l",))
+        barrier()
+        fleet_all.append(max_over_ranks(time.perf_counter() - t0))
+    fleet_s = min(fleet_all)
     fleet_ok = sum_over_ranks(float((fr["status"] == 0).sum()))
     # configs[4] "256 MC samples each": noisy closed-loop rollouts of every problem's optimised policy (Philox noise
     # coloured with chol(W)), host policy buffers in, J + per-problem statistics out
@@ -308,7 +311,7 @@ def main():
                              "solves_per_sec": THETAS / (ms1 * 1e-3)},
                "mpc_step": {"workload": f"configs[4]: fleet of {Pf} independent RAT iLQR unicycle problems per GPU (CE: 10 theta x 5 "
                                         "iterations + final solve), ratilqr_ce_solve_fleet, host buffers in, theta_opt/value/l out",
-                            "ms_per_fleet_step": fleet_s * 1e3, "problems_per_sec": Pf * world / fleet_s,
+                            "ms_per_fleet_step": fleet_s * 1e3, "ms_all": [t * 1e3 for t in fleet_all], "problems_per_sec": Pf * world / fleet_s,
                             "us_per_problem_step": fleet_s * 1e6 / (Pf * world), "ce_rounds": fr["rounds"],
                             "final_solves_ok": int(fleet_ok), "problems": Pf * world,
                             "mc_eval": {"samples_per_problem": MC, "ms": mc_s * 1e3, "rollouts_per_sec": MC * Pf * world / mc_s,

@@ -76,7 +76,16 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
       case 10: launch_shape<D, CT, 64, 7>(P, st); return;   // 144 regs, 14 warps/SM
       case 11: launch_shape<D, CT, 128, 3>(P, st); return;  // 168 regs, 128-thread CTAs
       case 12: launch_shape<D, CT, 64, 5>(P, st); return;   // 200 regs, 10 warps/SM
-      default: launch_shape<D, CT, 128, 3>(P, st); return;   // best of the sweeps in profiles/r01_tune_*.jsonl
+      default: {
+        // Throughput shape (168 registers, 12 warps/SM) once the batch exceeds what it keeps resident at a time; below
+        // that every instance is resident anyway and the 255-register build wins on latency (fewer spills, more ILP per
+        // thread): 7.3 vs 8.2 ms for 10-1024 solves, 39 vs 43 ms for a 56,830-instance CE round, equal at 82k
+        // (profiles/r01_shape_vs_batch.jsonl).
+        static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+        if ((size_t)P.B <= (size_t)sms * 384 && !P.queue) launch_shape<D, CT, 64, 4>(P, st);
+        else launch_shape<D, CT, 128, 3>(P, st);   // best of the sweeps in profiles/r01_tune_*.jsonl
+        return;
+      }
     }
   } else {
     launch_shape<D, CT, 64, 4>(P, st);
