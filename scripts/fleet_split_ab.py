@@ -32,7 +32,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 ref = None
-for k, order in (("1", "asc"), ("1", "desc"), ("2", "desc"), ("3", "desc"), ("4", "desc"), ("4", "asc")):
+for k, order in (("1", "desc"), ("2", "desc"), ("3", "desc"), ("4", "desc"), ("5", "desc"), ("6", "desc")):
     out = f"/tmp/fleet_split_{k}_{order}.npz"
     env = dict(os.environ, RATILQR_FLEET_SPLIT=k, RATILQR_FLEET_ORDER=order)
     line = subprocess.run([sys.executable, __file__, "--child", str(P), out], env=env, capture_output=True, text=True)
