@@ -190,6 +190,31 @@ def test_ce_fleet_on_device_matches_oracle_per_problem(gpu_be, oracle_be, kl, mu
 
 
 @pytest.mark.gpu
+def test_ce_fleet_philox_matches_injected_statistically(gpu_be):
+    """north_star: "match statistically (same elite theta distribution) with on-device RNG".  The same problem replicated
+    1,536 times: the CE runs driven by on-device Philox and the runs driven by injected host normals are two samples of
+    one distribution of (theta_opt, mu, sigma); compare their moments within sampling error."""
+    P = 1536
+    prob, x0, u = wl.c2_problem(N=20)
+    spec = prob.spec()
+    x0p = np.tile(x0[:, None], (1, P))
+    z = np.random.Generator(np.random.Philox(key=123)).standard_normal((P, 400))
+    kw = dict(num_samples=10, num_elite=3, iter_max=3, want=())
+    a = gpu_be.ce_solve_fleet(spec, x0p, u, 0.1, 1.0, 2.0, seed=2024, **kw)
+    b = gpu_be.ce_solve_fleet(spec, x0p, u, 0.1, 1.0, 2.0, z_inject=z, **kw)
+    c = gpu_be.ce_solve_fleet(spec, x0p, u, 0.1, 1.0, 2.0, seed=2024, **kw)
+    assert np.array_equal(a["theta_opt"], c["theta_opt"])  # same seed: bit-reproducible
+    assert np.std(a["theta_opt"]) > 0 and not np.array_equal(a["theta_opt"], b["theta_opt"])
+    for f in ("theta_opt", "mu", "sigma", "value"):
+        xa, xb = a[f], b[f]
+        se = np.sqrt(xa.var() / P + xb.var() / P)
+        assert abs(xa.mean() - xb.mean()) < 5 * se, f
+        assert abs(np.log(xa.std() / xb.std())) < 0.15, f
+    # the per-problem streams are distinct: problems do not share their draws
+    assert np.unique(a["theta_opt"]).size > 0.9 * P
+
+
+@pytest.mark.gpu
 def test_nm_fleet_on_device_matches_oracle_per_problem(gpu_be, oracle_be):
     """ratilqr_nm_solve_fleet (RAT iLQR++ for P problems in lock-step, speculative candidates) vs P independent runs of the
     oracle's restatement of solve!, including the persistence of the vertex costs across a second call."""
