@@ -93,6 +93,35 @@ def test_other_models(dut, oracle_be, name):
     assert (o["status"] == 0).sum() >= 8  # mostly feasible, with some neurotic breakdowns mixed in
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_problems_sweep(dut, oracle_be, seed):
+    """seeded random problems: random model of the registered set, dense SPD Q / R / Qf with a cross term Pc, stage-weight
+    ramp, dense SPD (sometimes time-varying) W, random x0 / u_init / horizon, theta spanning feasible and infeasible"""
+    rng = np.random.default_rng(1000 + seed)
+
+    def spd(k, scale):
+        a = rng.standard_normal((k, k))
+        return scale * (a @ a.T / k + np.eye(k))
+
+    f = [R.DoubleIntegrator(0.1), R.Pendulum(), R.Unicycle(0.1), R.CartPole(), R.SingleIntegrator(0.5)][seed % 5]
+    n, m = f.n, f.m
+    N = int(rng.integers(5, 26))
+    xg = 0.5 * rng.standard_normal(n)
+    cost = R.QuadraticCost(n, m, Q=spd(n, 0.05), R=spd(m, 0.05), Qf=spd(n, 0.5), xg=xg, Pc=0.01 * rng.standard_normal((n, m)),
+                           ws0=1.0, ws1=float(rng.choice([0.0, 0.05])), c0=0.3, c1=0.01, h0=0.2)
+    if seed % 2:
+        Ws = np.stack([spd(n, 1e-3) * (1.0 + 0.05 * k) for k in range(N)])
+        Wf = lambda k: Ws[k]
+    else:
+        Wf = R.ConstantCovariance(spd(n, 1e-3))
+    prob = R.FiniteHorizonRiskSensitiveOptimalControlProblem(f, cost.c, cost.h, Wf, N)
+    x0 = 0.3 * rng.standard_normal(n) + (np.array([0, 0, 0, 1.0])[:n] if isinstance(f, type(R.Unicycle(0.1))) and n == 4 else 0)
+    u = 0.05 * rng.standard_normal((m, N))
+    theta = np.concatenate([[0.0], np.abs(rng.standard_normal(11)) * 10.0 ** rng.uniform(-2, 1.5, 11)])
+    g, o = check_solve(dut, oracle_be, prob.spec(), x0, u, theta, opts=R.make_opts(iter_max=30))
+    assert (o["status"] == 0).any()
+
+
 def test_quadrotor_small(dut, oracle_be):
     prob, x0, u = wl.c3_problem(N=10)
     check_solve(dut, oracle_be, prob.spec(), x0, u, [0.0, 0.05, 0.5], opts=R.make_opts(iter_max=6))
