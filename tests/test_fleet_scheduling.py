@@ -68,3 +68,32 @@ def test_sub_fleet_blocks_reproduce_the_one_block_solve(blocks):
         for f in ("theta_opt", "value", "theta_min", "theta_max", "mu", "sigma", "mu_init", "sigma_init", "nz_used", "status",
                   "iters", "x", "l", "L"):
             assert np.array_equal(a[f], b[f]), f
+
+
+@pytest.mark.gpu
+def test_cp_async_staging_is_transparent():
+    """the thread-private cp.async staging (two rollout stages in flight over two shared-memory buffers whose contents go
+    to registers before the buffer is reused) must not change a single bit: compare with RATILQR_NO_STAGE=1 (plain loads)
+    on a batch of several resident waves, i.e. under the memory pressure where a too-early buffer reuse would show"""
+    P, K = 160, 1024
+    prob, cps, x0, u = wl.fleet(P, key=5)
+    spec = prob.spec(cost_params=cps)
+    theta = np.concatenate([wl.positive_thetas(K, key=300 + p) for p in range(P)])
+    old = os.environ.get("RATILQR_NO_STAGE")
+    res = {}
+    try:
+        for flag in ("0", "1"):
+            os.environ["RATILQR_NO_STAGE"] = flag
+            be = R.new_backend(0)
+            try:
+                res[flag] = be.ileqg_solve_batch(spec, x0, u, theta, P=P, want=("l",))
+            finally:
+                be.close()
+    finally:
+        if old is None:
+            os.environ.pop("RATILQR_NO_STAGE", None)
+        else:
+            os.environ["RATILQR_NO_STAGE"] = old
+    for f in ("status", "iters", "trials", "restarts", "value", "mu", "d_current", "l"):
+        assert np.array_equal(res["0"][f], res["1"][f], equal_nan=True) if res["0"][f].dtype.kind == "f" else np.array_equal(res["0"][f], res["1"][f]), f
+    assert (res["0"]["status"] == 0).sum() > 0.9 * P * K
