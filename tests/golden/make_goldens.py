@@ -43,3 +43,21 @@ prob, x0, u = wl.c3_problem(N=12)
 th = np.array([0.0, 0.05, 0.5])
 save("c3_quadrotor_N12.npz", dict(x0=x0, u=u, theta=th), o.ileqg_solve_batch(prob.spec(), x0, u, th))
 print("goldens written to", HERE)
+
+# user-extensible models: the drag-car dynamics + obstacle cost snippets of tests/user_models/ (no registered
+# equivalent, so no oracle): frozen from the g++ build of the snippets (tests/_hostemu), which is itself checked against
+# complex-step / finite-difference derivatives of a numpy restatement (tests/test_user_models.py)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _hostemu  # noqa: E402
+from ratilqr_b200 import _capi  # noqa: E402
+
+h = _hostemu.load()
+prob, x0, u = wl.c2_problem(N=30)
+ref = prob.spec()
+QD, RD, XG = np.array([1.0, 1.0, 0.1, 0.1]), np.array([0.1, 0.1]), np.array([5.0, 5.0, 0.0, 0.0])
+obst_cp = np.concatenate([0.01 * QD, 0.01 * RD, XG, [10.0], [2.5, 2.0, 0.8, 0.3]])
+drag_p = np.array([0.1, 0.05, 1.5])
+spec = _capi.Spec(1001, 101, 4, 2, 30, drag_p, obst_cp, ref.W.reshape(4, 4, order="F"))  # hostemu numbering of the snippets
+th = np.concatenate([[0.0], wl.positive_thetas(15, key=21)])
+save("user_dragcar_obstacle.npz", dict(x0=x0, u=u, theta=th, cost_params=obst_cp, model_params=drag_p, W=ref.W.reshape(4, 4, order="F")),
+     h.ileqg_solve_batch(spec, x0, u, th))

@@ -395,3 +395,31 @@ def test_gpu_user_model_through_reference_api(gpu_be):
     ce = R.CrossEntropyBilevelOptimizationSolver(num_samples=8, num_elite=3, iter_max=2, backend=gpu_be)
     out = R.cross_entropy.solve_(ce, prob, x0, u0, np.random.default_rng(1), kl_bound=0.1, verbose=False)
     assert out[0] > 0 and np.isfinite(out[4])
+
+
+def _golden_user_case():
+    g = np.load(os.path.join(HERE, "golden", "user_dragcar_obstacle.npz"))
+    return g, (4, 2, 30, g["model_params"], g["cost_params"], g["W"])
+
+
+def _check_against_golden(r, g):
+    for k in ("status", "iters", "trials", "restarts"):
+        assert np.array_equal(r[k], g[k]), k
+    ok = g["status"] == 0
+    assert ok.sum() >= 8
+    for k in ("value", "x", "l", "L"):
+        assert relerr(r[k][..., ok], g[k][..., ok]) < RTOL, k
+
+
+def test_hostemu_user_model_golden(hostemu_be):
+    """frozen result of the drag-car + obstacle-cost solve (tests/golden/make_goldens.py): pins the dual-number adapters"""
+    g, (n, m, N, mp, cp, W) = _golden_user_case()
+    r = hostemu_be.ileqg_solve_batch(_capi.Spec(HM_DRAGCAR, HM_OBSTACLE, n, m, N, mp, cp, W), g["x0"], g["u"], g["theta"])
+    _check_against_golden(r, g)
+
+
+@pytest.mark.gpu
+def test_gpu_user_model_golden(gpu_be, gpu_user):
+    g, (n, m, N, mp, cp, W) = _golden_user_case()
+    r = gpu_be.ileqg_solve_batch(_capi.Spec(gpu_user["drag+obst"], _capi.COST_USER, n, m, N, mp, cp, W), g["x0"], g["u"], g["theta"])
+    _check_against_golden(r, g)
