@@ -82,7 +82,7 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
         // thread): 7.3 vs 8.2 ms for 10-1024 solves, 39 vs 43 ms for a 56,830-instance CE round, equal at 82k
         // (profiles/r01_shape_vs_batch.jsonl).
         static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
-        if ((size_t)P.B <= (size_t)sms * 384 && !P.queue) launch_shape<D, CT, 64, 4>(P, st);
+        if ((size_t)P.B <= (size_t)sms * 384 && !P.queue) launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4>(P, st);  // + constants pinned in L1
         else launch_shape<D, CT, 128, 3>(P, st);   // best of the sweeps in profiles/r01_tune_*.jsonl
         return;
       }
