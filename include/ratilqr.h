@@ -217,6 +217,16 @@ int32_t ratilqr_riccati_batch(ratilqr_ctx* ctx, int32_t n, int32_t m, int32_t N,
                               double mu_min, double delta_0, double* mu, double* delta,
                               double* L, double* dl,
                               double* s, double* sv, double* S, int32_t* status, int32_t* restarts);
+/* same with a time-varying noise covariance: W is n*n*N when W_time_varying != 0 and stage k uses
+ * W(k) = W[:, :, k] exactly as ileqg.jl:364,438 index approx_result.W_array[ii] */
+int32_t ratilqr_riccati_batch_tv(ratilqr_ctx* ctx, int32_t n, int32_t m, int32_t N, int32_t B,
+                                 int32_t optimise,
+                                 const double* q, const double* qv, const double* Q, const double* r,
+                                 const double* R, const double* Pm, const double* A, const double* Bm,
+                                 const double* W, int32_t W_time_varying, const double* theta,
+                                 double mu_min, double delta_0, double* mu, double* delta,
+                                 double* L, double* dl,
+                                 double* s, double* sv, double* S, int32_t* status, int32_t* restarts);
 
 /* ---- noisy closed-loop Monte Carlo rollouts ----------------------------------------
  * simulate_dynamics(problem, x_array, l_array, L_array, rng) + integrate_cost

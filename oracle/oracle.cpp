@@ -878,14 +878,29 @@ int32_t oracle_linearize_batch(void*, const ratilqr_problem_desc* desc, int32_t 
   return 0;
 }
 
-int32_t oracle_riccati_batch(void*, int32_t n, int32_t m, int32_t N, int32_t B, int32_t optimise,
+int32_t oracle_riccati_batch_tv(void*, int32_t n, int32_t m, int32_t N, int32_t B, int32_t optimise,
+                                const double* q, const double* qv, const double* Q, const double* r, const double* R,
+                                const double* Pm, const double* A, const double* Bm, const double* W,
+                                int32_t W_time_varying, const double* theta, double mu_min, double delta_0, double* mu,
+                                double* delta, double* L, double* dl, double* s, double* sv, double* S, int32_t* status,
+                                int32_t* restarts);
+int32_t oracle_riccati_batch(void* c, int32_t n, int32_t m, int32_t N, int32_t B, int32_t optimise,
                              const double* q, const double* qv, const double* Q, const double* r, const double* R,
                              const double* Pm, const double* A, const double* Bm, const double* W,
                              const double* theta, double mu_min, double delta_0, double* mu, double* delta,
                              double* L, double* dl, double* s, double* sv, double* S, int32_t* status,
                              int32_t* restarts) {
+  return oracle_riccati_batch_tv(c, n, m, N, B, optimise, q, qv, Q, r, R, Pm, A, Bm, W, 0, theta, mu_min, delta_0, mu, delta,
+                                 L, dl, s, sv, S, status, restarts);
+}
+int32_t oracle_riccati_batch_tv(void*, int32_t n, int32_t m, int32_t N, int32_t B, int32_t optimise,
+                                const double* q, const double* qv, const double* Q, const double* r, const double* R,
+                                const double* Pm, const double* A, const double* Bm, const double* W,
+                                int32_t W_time_varying, const double* theta, double mu_min, double delta_0, double* mu,
+                                double* delta, double* L, double* dl, double* s, double* sv, double* S, int32_t* status,
+                                int32_t* restarts) {
   WSet ws;
-  if (!prep_Wset(n, N, W, 0, ws)) return -2;
+  if (!prep_Wset(n, N, W, W_time_varying, ws)) return -2;
   for (int b = 0; b < B; ++b) {
     Approx ap;
     ap.resize(n, m, N);

@@ -176,8 +176,8 @@ class CApi:
         self.f_closed = self._fn("rollout_closed_batch", [vp, PD, i32, dp, dp, dp, dp, dp, ip])
         self.f_cost = self._fn("integrate_cost_batch", [vp, PD, i32, dp, dp, dp, ip])
         self.f_lin = self._fn("linearize_batch", [vp, PD, i32, dp, dp] + [dp] * 8 + [ip])
-        self.f_ric = self._fn("riccati_batch", [vp, i32, i32, i32, i32, i32] + [dp] * 8 + [dp, dp, f64, f64, dp, dp,
-                                                                                          dp, dp, dp, dp, dp, ip, ip])
+        self.f_ric = self._fn("riccati_batch_tv", [vp, i32, i32, i32, i32, i32] + [dp] * 8 + [dp, i32, dp, f64, f64, dp, dp,
+                                                                                             dp, dp, dp, dp, dp, ip, ip])
         self.f_mc = self._fn("mc_rollout", [vp, PD, i32, dp, dp, dp, i32, dp, C.c_uint64, f64, dp, dp, dp])
         self.f_mc_true = self._fn("mc_rollout_true_model", [vp, PD, i32, dp, dp, dp, i32, C.POINTER(NoiseMixture), C.c_uint64,
                                                             f64, dp, dp, dp])
@@ -492,7 +492,12 @@ class CApi:
         theta = np.ascontiguousarray(np.broadcast_to(np.asarray(theta, dtype=np.float64), (B,)))
         mu_a = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, dtype=np.float64), (B,))).copy()
         de_a = np.ascontiguousarray(np.broadcast_to(np.asarray(delta, dtype=np.float64), (B,))).copy()
-        Wf = _f64(W)
+        # W: one n x n matrix, or n x n x N (W(k) per stage, ileqg.jl:364,438)
+        Wa = np.asarray(W, dtype=np.float64)
+        W_tv = 1 if Wa.ndim == 3 else 0
+        if W_tv:
+            assert Wa.shape == (n, n, N), "time-varying W must be n x n x N"
+        Wf = _f64(Wa)
         arrs = [_f64(lin[k]) for k in ("q", "qv", "Q", "r", "R", "P", "A", "B")]
         if optimise:
             Lf = np.zeros(m * n * N * B)
@@ -505,7 +510,7 @@ class CApi:
         S = np.zeros((n, n, N + 1, B), order="F")
         st = np.zeros(B, np.int32)
         rs = np.zeros(B, np.int32)
-        self._check(self.f_ric(self.ctx, n, m, N, B, int(optimise), *[_dp(a) for a in arrs], _dp(Wf), _dp(theta),
+        self._check(self.f_ric(self.ctx, n, m, N, B, int(optimise), *[_dp(a) for a in arrs], _dp(Wf), W_tv, _dp(theta),
                                float(mu_min), float(delta_0), _dp(mu_a), _dp(de_a), _dp(Lf), _dp(dlf),
                                _dp(s), _dp(sv), _dp(S), _ip(st), _ip(rs)), "riccati_batch")
         return dict(s=s, sv=sv, S=S, status=st, restarts=rs, mu=mu_a, delta=de_a,

@@ -151,7 +151,9 @@ def solve_(ce, problem, x_0, u_array, rng, verbose=False, serial=False, **kw):
             ileqg = ILEQGSolver(problem, backend=ce._be(), **ce.ileqg_kwargs())
             x_array, l_array, L_array, value, _ = ileqg_solve_(ileqg, problem, x_0, u_array, theta=theta_opt, verbose=False)
             if kl_bound > 0:
-                return theta_opt, x_array, l_array, L_array, value + kl_bound / theta_opt, theta_min, theta_max
+                # Julia: kl_bound/0.0 == Inf (the retry rule can drive θ_opt to 0.0, :410-413); Python would raise
+                kl_term = kl_bound / theta_opt if theta_opt > 0 else math.inf
+                return theta_opt, x_array, l_array, L_array, value + kl_term, theta_min, theta_max
             return theta_opt, x_array, l_array, L_array, value, 0.0, 0.0
         except (AssertionError, ValueError, RuntimeError):
             if verbose:

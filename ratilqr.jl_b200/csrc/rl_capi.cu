@@ -780,6 +780,16 @@ int32_t ratilqr_riccati_batch(ratilqr_ctx* ctx, int32_t n_, int32_t m_, int32_t 
                               const double* Pm, const double* A, const double* Bm, const double* W, const double* theta,
                               double mu_min, double delta_0, double* mu, double* delta, double* L, double* dl,
                               double* s, double* sv, double* S, int32_t* status, int32_t* restarts) {
+  return ratilqr_riccati_batch_tv(ctx, n_, m_, N_, B, optimise, q, qv, Q, r, R, Pm, A, Bm, W, 0, theta, mu_min, delta_0, mu,
+                                  delta, L, dl, s, sv, S, status, restarts);
+}
+
+int32_t ratilqr_riccati_batch_tv(ratilqr_ctx* ctx, int32_t n_, int32_t m_, int32_t N_, int32_t B, int32_t optimise,
+                                 const double* q, const double* qv, const double* Q, const double* r, const double* R,
+                                 const double* Pm, const double* A, const double* Bm, const double* W,
+                                 int32_t W_time_varying, const double* theta, double mu_min, double delta_0, double* mu,
+                                 double* delta, double* L, double* dl, double* s, double* sv, double* S, int32_t* status,
+                                 int32_t* restarts) {
   if (!ctx) return -1;
   if (B < 1 || N_ < 1 || !q || !qv || !Q || !r || !R || !Pm || !A || !Bm || !W || !theta || !mu || !delta || !L || !s || !sv || !S)
     FAIL(-1, "null argument");
@@ -788,11 +798,12 @@ int32_t ratilqr_riccati_batch(ratilqr_ctx* ctx, int32_t n_, int32_t m_, int32_t 
   CU(cudaSetDevice(ctx->device));
   const size_t n = n_, m = m_, N = N_;
   rlh::WPrep wp;
-  if (!rlh::prep_W(n_, N_, W, 0, wp)) FAIL(-2, "W is not positive definite");
+  if (!rlh::prep_W(n_, N_, W, W_time_varying, wp)) FAIL(-2, "W(k) is not positive definite");
   const size_t sz[8] = {(N + 1) * B, n * (N + 1) * B, n * n * (N + 1) * B, m * N * B, m * m * N * B, m * n * N * B, n * n * N * B, n * m * N * B};
   const double* ins[8] = {q, qv, Q, r, R, Pm, A, Bm};
   for (int i = 0; i < 8; ++i) UP(ctx->s[i], ins[i], sz[i] * 8);
-  UP(ctx->d_W, wp.W.data(), n * n * 8); UP(ctx->d_Winv, wp.Winv.data(), n * n * 8);
+  UP(ctx->d_W, wp.W.data(), wp.W.size() * 8); UP(ctx->d_Winv, wp.Winv.data(), wp.Winv.size() * 8);
+  UP(ctx->d_detW, wp.detW.data(), wp.detW.size() * 8);
   UP(ctx->s[8], theta, (size_t)B * 8); UP(ctx->s[9], mu, (size_t)B * 8); UP(ctx->s[10], delta, (size_t)B * 8);
   if (optimise) { CU(ctx->s[11].reserve(m * n * N * B * 8)); CU(ctx->s[12].reserve(m * N * B * 8)); }
   else { UP(ctx->s[11], L, m * n * N * B * 8); if (dl) UP(ctx->s[12], dl, m * N * B * 8); }
@@ -803,7 +814,7 @@ int32_t ratilqr_riccati_batch(ratilqr_ctx* ctx, int32_t n_, int32_t m_, int32_t 
   a.n = n_; a.m = m_; a.N = N_; a.B = B; a.optimise = optimise;
   a.q = ctx->s[0].as<double>(); a.qv = ctx->s[1].as<double>(); a.Q = ctx->s[2].as<double>(); a.r = ctx->s[3].as<double>();
   a.R = ctx->s[4].as<double>(); a.Pm = ctx->s[5].as<double>(); a.A = ctx->s[6].as<double>(); a.Bm = ctx->s[7].as<double>();
-  a.W = ctx->d_W.as<double>(); a.Winv = ctx->d_Winv.as<double>(); a.detW = wp.detW[0];
+  a.W = ctx->d_W.as<double>(); a.Winv = ctx->d_Winv.as<double>(); a.detW = ctx->d_detW.as<double>(); a.W_tv = W_time_varying ? 1 : 0;
   a.theta = ctx->s[8].as<double>(); a.mu_min = mu_min; a.delta_0 = delta_0;
   a.mu = ctx->s[9].as<double>(); a.delta = ctx->s[10].as<double>(); a.L = ctx->s[11].as<double>(); a.dl = ctx->s[12].as<double>();
   a.has_dl = dl != nullptr;
@@ -1004,6 +1015,8 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
   if (!(kl_bound >= 0)) FAIL(-3, "KL Divergence Bound must be non-negative");  // :368
   if (ce->num_samples < 1 || ce->num_elite < 1 || ce->num_elite > ce->num_samples || ce->iter_max < 1) FAIL(-3, "bad CE options");
   const int S = ce->num_samples;
+  // sub-fleet blocks run on fresh host threads whose current device is 0: bind before any allocation / copy
+  CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   // per-problem CE state on the device (scratch slots s[0..12] are free during a solve)
   rll::CeFleet c;
@@ -1203,6 +1216,7 @@ int32_t ratilqr_nm_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   if (!ctx) return -1;
   if (!nm || P < 1 || !theta_high_init || !theta_low_init || !c_high || !c_low || !has_c || !theta_opt || !value) FAIL(-1, "bad arguments");
   if (!(kl_bound >= 0)) FAIL(-3, "KL Divergence Bound must be non-negative");  // :280
+  CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   rll::NmFleet c;
   memset(&c, 0, sizeof(c));

@@ -132,8 +132,9 @@ RL_HD int comp_linearize_stage(const double* mp, const double* cp, int N, int k,
 template <int n, int m>
 RL_HD int comp_riccati(int N, int optimise, const double* q, const double* qv, const double* Q, const double* r,
                        const double* R, const double* Pm, const double* A, const double* Bm, const double* W,
-                       const double* Winv, double detW, double theta, double mu_min, double delta_0, double* mu,
+                       const double* Winv, const double* detWs, int W_tv, double theta, double mu_min, double delta_0, double* mu,
                        double* delta, double* L, double* dl, double* s, double* sv, double* S, int32_t* restarts) {
+  // W_tv: W, Winv are n*n*N and detWs has N entries (W(k) of stage k, ileqg.jl:364,438); else one shared matrix
   int nrestart = 0;
   while (true) {
     double Sc[n * n], svc[n], sc;
@@ -155,15 +156,18 @@ RL_HD int comp_riccati(int N, int optimise, const double* q, const double* qv, c
       for (int i = 0; i < m * m; ++i) Rl[i] = R[(size_t)k * m * m + i];
       for (int i = 0; i < m * n; ++i) { Pl[i] = Pm[(size_t)k * m * n + i]; Bl[i] = Bm[(size_t)k * n * m + i]; }
       int rc;
+      const double* Wk = W + (W_tv ? (size_t)k * n * n : 0);
+      const double* Wik = Winv + (W_tv ? (size_t)k * n * n : 0);
+      const double detW = detWs[W_tv ? k : 0];
       if (optimise) {
-        rc = riccati_stage<DenseTraits<n, m>, true, true>(theta, *mu, W, Winv, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
+        rc = riccati_stage<DenseTraits<n, m>, true, true>(theta, *mu, Wk, Wik, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
       } else {
         for (int i = 0; i < m * n; ++i) Ll[i] = L[(size_t)k * m * n + i];
         if (dl) {
           for (int i = 0; i < m; ++i) dll[i] = dl[(size_t)k * m + i];
-          rc = riccati_stage<DenseTraits<n, m>, false, true>(theta, *mu, W, Winv, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
+          rc = riccati_stage<DenseTraits<n, m>, false, true>(theta, *mu, Wk, Wik, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
         } else {
-          rc = riccati_stage<DenseTraits<n, m>, false, false>(theta, *mu, W, Winv, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
+          rc = riccati_stage<DenseTraits<n, m>, false, false>(theta, *mu, Wk, Wik, detW, Sc, svc, sc, q[k], qvl, Ql, rl_, Rl, Pl, Al, Bl, Ll, dll);
         }
       }
       if (rc == 1) { *restarts = nrestart; return optimise ? RATILQR_ST_M_NOT_PD_OPT : RATILQR_ST_M_NOT_PD_INIT; }

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(64) k_riccati(RiccatiArgs a) {
   int st = comp_riccati<n, m>(N, a.optimise, a.q + (size_t)b * (N + 1), a.qv + (size_t)b * n * (N + 1),
                               a.Q + (size_t)b * n * n * (N + 1), a.r + (size_t)b * m * N, a.R + (size_t)b * m * m * N,
                               a.Pm + (size_t)b * m * n * N, a.A + (size_t)b * n * n * N, a.Bm + (size_t)b * n * m * N,
-                              a.W, a.Winv, a.detW, a.theta[b], a.mu_min, a.delta_0, &mu, &delta,
+                              a.W, a.Winv, a.detW, a.W_tv, a.theta[b], a.mu_min, a.delta_0, &mu, &delta,
                               a.L + (size_t)b * m * n * N, (a.optimise || a.has_dl) ? a.dl + (size_t)b * m * N : nullptr,
                               a.s + (size_t)b * (N + 1), a.sv + (size_t)b * n * (N + 1),
                               a.S + (size_t)b * n * n * (N + 1), &nr);

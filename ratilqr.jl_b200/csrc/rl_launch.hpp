@@ -35,7 +35,8 @@ int launch_linearize(const CompArgs& a, cudaStream_t st);
 struct RiccatiArgs {
   int n, m, N, B, optimise;
   const double *q, *qv, *Q, *r, *R, *Pm, *A, *Bm, *W, *Winv;
-  double detW;
+  const double* detW;  // device: 1 or N determinants
+  int W_tv;
   const double* theta;
   double mu_min, delta_0;
   double *mu, *delta, *L, *dl, *s, *sv, *S;

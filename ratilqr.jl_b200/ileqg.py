@@ -57,6 +57,15 @@ def _stack(v):  # list of vectors/matrices -> array with the list index last
     return np.stack([np.asarray(e, dtype=np.float64) for e in v], axis=-1)
 
 
+def _W_arg(W_array):
+    """W_array of an ApproximationResult -> one n x n matrix when W(k) is constant, else n x n x N (stage k uses W(k),
+    ileqg.jl:364,438)."""
+    W0 = W_array[0]
+    if all(np.array_equal(W0, w) for w in W_array[1:]):
+        return W0
+    return _stack(W_array)
+
+
 class ILEQGSolver:  # ileqg.jl:164-208
     def __init__(self, problem, backend=None, **kw):
         kw = _ascii_kw(kw)
@@ -194,7 +203,7 @@ def solve_approximate_dp_(ileqg, approx_result, verbose=False, backend=None, **k
     """solve_approximate_dp! (ileqg.jl:341-406): optimises L (stored into ileqg.L_array) and dl."""
     theta = _ascii_kw(kw)["theta"]
     be = backend or ileqg._be()
-    r = be.riccati(approx_result._lin, approx_result.W_array[0], theta, True, mu=ileqg.mu, delta=ileqg.delta,
+    r = be.riccati(approx_result._lin, _W_arg(approx_result.W_array), theta, True, mu=ileqg.mu, delta=ileqg.delta,
                    mu_min=ileqg.mu_min, delta_0=ileqg.delta_0)
     if r["status"][0] != 0:
         raise NotPositiveDefinite(_STATUS_MSG[2])
@@ -211,7 +220,7 @@ def solve_approximate_dp(approx_result, L_array, dl_array=None, backend=None, **
     assert N == len(L_array)
     if dl_array is not None:
         assert N == len(dl_array)
-    r = be.riccati(approx_result._lin, approx_result.W_array[0], kw["theta"], False,
+    r = be.riccati(approx_result._lin, _W_arg(approx_result.W_array), kw["theta"], False,
                    L=_stack(L_array)[..., None], dl=None if dl_array is None else _stack(dl_array)[..., None],
                    mu=kw["mu"])
     if r["status"][0] != 0:
@@ -322,7 +331,9 @@ def solve_(ileqg, problem, x_0, u_array, verbose=False, backend=None, **kw):
     theta = float(_ascii_kw(kw)["theta"])
     be = backend or ileqg._be()
     spec = problem.spec()
-    cap = max(16, 4 * ileqg.iter_max)
+    # ϵ_history holds one entry per merit evaluation: up to ceil(log(ϵ_min/ϵ_init)/log(λ)) + 1 trials per iteration (:537)
+    per_iter = int(math.ceil(math.log(ileqg.eps_min / ileqg.eps_init_init) / math.log(ileqg.lam))) + 2
+    cap = max(16, ileqg.iter_max * per_iter)
     r = be.ileqg_solve_batch(spec, np.asarray(x_0, float), _stack(u_array), [theta], opts=ileqg.opts(),
                              eps_hist_cap=cap)
     raise_for_status(r["status"][0])
@@ -330,7 +341,9 @@ def solve_(ileqg, problem, x_0, u_array, verbose=False, backend=None, **kw):
     ileqg.L_array = _mats(r["L"][..., 0])
     ileqg.value_current = float(r["value"][0])
     ileqg.iter_current, ileqg.d_current, ileqg.mu = int(r["iters"][0]), float(r["d_current"][0]), float(r["mu"][0])
-    nt = min(int(r["trials"][0]), cap)
+    nt = int(r["trials"][0])
+    if nt > cap:
+        raise RuntimeError(f"ϵ_history overflow: {nt} line-search trials > capacity {cap}")
     ileqg.eps_history = [(float(r["eps_hist"][0, i, 0]), float(r["eps_hist"][1, i, 0])) for i in range(nt)]
     if verbose:
         print(f"ILEQG finished: iterations {ileqg.iter_current}, value {ileqg.value_current:.6g}, d == {ileqg.d_current:.3g}")

@@ -91,14 +91,14 @@ template <class F> static int dispatch(int model_id, int cost_id, F&& fn) {
 
 template <int n, int m>
 static void ric(int N, int B, int optimise, const double* q, const double* qv, const double* Q, const double* r,
-                const double* R, const double* Pm, const double* A, const double* Bm, const rlh::WPrep& wp,
+                const double* R, const double* Pm, const double* A, const double* Bm, const rlh::WPrep& wp, int W_tv,
                 const double* theta, double mu_min, double delta_0, double* mu, double* delta, double* L, double* dl,
                 double* s, double* sv, double* S, int32_t* status, int32_t* restarts) {
   for (int b = 0; b < B; ++b) {
     int32_t nr = 0;
     int st = comp_riccati<n, m>(N, optimise, q + (size_t)b * (N + 1), qv + (size_t)b * n * (N + 1), Q + (size_t)b * n * n * (N + 1),
                                 r + (size_t)b * m * N, R + (size_t)b * m * m * N, Pm + (size_t)b * m * n * N,
-                                A + (size_t)b * n * n * N, Bm + (size_t)b * n * m * N, wp.W.data(), wp.Winv.data(), wp.detW[0],
+                                A + (size_t)b * n * n * N, Bm + (size_t)b * n * m * N, wp.W.data(), wp.Winv.data(), wp.detW.data(), W_tv,
                                 theta[b], mu_min, delta_0, &mu[b], &delta[b], L + (size_t)b * m * n * N,
                                 dl ? dl + (size_t)b * m * N : nullptr, s + (size_t)b * (N + 1), sv + (size_t)b * n * (N + 1),
                                 S + (size_t)b * n * n * (N + 1), &nr);
@@ -303,14 +303,28 @@ int32_t hostemu_linearize_batch(void*, const ratilqr_problem_desc* d, int32_t B,
   });
 }
 
-int32_t hostemu_riccati_batch(void*, int32_t n, int32_t m, int32_t N, int32_t B, int32_t optimise, const double* q,
+int32_t hostemu_riccati_batch_tv(void*, int32_t n, int32_t m, int32_t N, int32_t B, int32_t optimise, const double* q,
+                                 const double* qv, const double* Q, const double* r, const double* R, const double* Pm,
+                                 const double* A, const double* Bm, const double* W, int32_t W_tv, const double* theta,
+                                 double mu_min, double delta_0, double* mu, double* delta, double* L, double* dl, double* s,
+                                 double* sv, double* S, int32_t* status, int32_t* restarts);
+int32_t hostemu_riccati_batch(void* c, int32_t n, int32_t m, int32_t N, int32_t B, int32_t optimise, const double* q,
                               const double* qv, const double* Q, const double* r, const double* R, const double* Pm,
                               const double* A, const double* Bm, const double* W, const double* theta, double mu_min,
                               double delta_0, double* mu, double* delta, double* L, double* dl, double* s, double* sv,
                               double* S, int32_t* status, int32_t* restarts) {
+  return hostemu_riccati_batch_tv(c, n, m, N, B, optimise, q, qv, Q, r, R, Pm, A, Bm, W, 0, theta, mu_min, delta_0, mu, delta, L,
+                                  dl, s, sv, S, status, restarts);
+}
+int32_t hostemu_riccati_batch_tv(void*, int32_t n, int32_t m, int32_t N, int32_t B, int32_t optimise, const double* q,
+                                 const double* qv, const double* Q, const double* r, const double* R, const double* Pm,
+                                 const double* A, const double* Bm, const double* W, int32_t W_tv, const double* theta,
+                                 double mu_min, double delta_0, double* mu, double* delta, double* L, double* dl, double* s,
+                                 double* sv, double* S, int32_t* status, int32_t* restarts) {
   rlh::WPrep wp;
-  if (!rlh::prep_W(n, N, W, 0, wp)) return -2;
-#define R_(NN, MM) if (n == NN && m == MM) { ric<NN, MM>(N, B, optimise, q, qv, Q, r, R, Pm, A, Bm, wp, theta, mu_min, delta_0, mu, delta, L, dl, s, sv, S, status, restarts); return 0; }
+  W_tv = W_tv ? 1 : 0;
+  if (!rlh::prep_W(n, N, W, W_tv, wp)) return -2;
+#define R_(NN, MM) if (n == NN && m == MM) { ric<NN, MM>(N, B, optimise, q, qv, Q, r, R, Pm, A, Bm, wp, W_tv, theta, mu_min, delta_0, mu, delta, L, dl, s, sv, S, status, restarts); return 0; }
   R_(2, 2) R_(2, 1) R_(4, 2) R_(4, 1) R_(12, 4)
 #undef R_
   return -5;
