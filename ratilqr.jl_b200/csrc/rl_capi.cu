@@ -46,6 +46,7 @@ struct ratilqr_ctx {
   int model_id = 0, cost_id = 0, n = 0, m = 0, N = 0, B = 0, eps_cap = 0;
   bool coop = false;          // staged solve runs on the warp-cooperative kernel
   bool dynamic = false;       // staged solve uses the persistent kernel with lane-level refill
+  int spec_G = 0;             // > 0: staged solve runs on the speculative latency kernel with this many lanes per instance
   bool traj_retained = false; // xo/lo/Lo hold the trajectories (coop / dynamic modes)
   DBuf d_queue;
   int coop_cost_id = 0;
@@ -209,11 +210,33 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   UP(ctx->d_u, in->u_init, (size_t)m * N * in->u_count * 8);
   if (device_theta) CU(ctx->d_theta.reserve(B * 8));  // theta is produced on the device (fleet CE)
   else UP(ctx->d_theta, in->theta, B * 8);
-  const size_t Bp = (B + 31) / 32 * 32;  // the workspace is tiled in groups of 32 thread slots
+  // Kernel choice, part 1: a batch that leaves most of the machine idle runs on the speculative latency kernel
+  // (rl_spec.cuh): G lanes per instance evaluate several line-search candidates at once and run the next iteration's
+  // optimising pass alongside each candidate's evaluating pass.  G = 8 while every warp still gets a scheduler of its own
+  // (148 SMs x 4), G = 4 up to twice that; beyond, lanes are worth more as instances (one thread per instance).
+  ctx->spec_G = 0;
+  {
+    const int cid = (!um && rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const size_t warps1 = (size_t)sms * 4;
+    const char* e = getenv("RATILQR_SPEC");  // 0 = off, 2 / 4 / 8 = force that many lanes per instance (tuning / A-B runs)
+    int G = 0;
+    if (e) G = atoi(e);
+    else if (B * 8 <= warps1 * 32) G = 8;
+    else if (B * 4 <= warps1 * 64) G = 4;
+    if (G != 2 && G != 4 && G != 8) G = 0;
+    const char* ed = getenv("RATILQR_DYNAMIC");
+    const char* ec = getenv("RATILQR_COOP");
+    if (!um && n <= 6 && G && rll::spec_supported(desc->model_id, cid) && !(ed && ed[0] == '1') && !(ec && ec[0] == '1')) ctx->spec_G = G;
+  }
+  const size_t cols = ctx->spec_G ? B * ctx->spec_G : B;  // workspace columns: one per thread
+  const size_t pol = ctx->spec_G ? 2 : 1;                 // the speculative kernel double-buffers the policy (Lg, DL)
+  const size_t Bp = (cols + 31) / 32 * 32;  // the workspace is tiled in groups of 32 thread slots
   CU(ctx->d_X.reserve(2 * (size_t)(N + 1) * n * Bp * 8));
   CU(ctx->d_U.reserve(2 * (size_t)N * m * Bp * 8));
-  CU(ctx->d_Lg.reserve((size_t)N * m * n * Bp * 8));
-  CU(ctx->d_DL.reserve((size_t)N * m * Bp * 8));
+  CU(ctx->d_Lg.reserve(pol * (size_t)N * m * n * Bp * 8));
+  CU(ctx->d_DL.reserve(pol * (size_t)N * m * Bp * 8));
   CU(ctx->d_value.reserve(B * 8));
   CU(ctx->d_mu.reserve(B * 8));
   CU(ctx->d_d.reserve(B * 8));
@@ -227,7 +250,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
     CU(cudaMemsetAsync(ctx->d_eps.p, 0, B * eps_cap * 16, ctx->stream));
   }
   // gains of instances that fail before their first optimising pass stay zero (initialize!: L = 0)
-  CU(cudaMemsetAsync(ctx->d_Lg.p, 0, (size_t)N * m * n * Bp * 8, ctx->stream));
+  if (!ctx->spec_G) CU(cudaMemsetAsync(ctx->d_Lg.p, 0, (size_t)N * m * n * Bp * 8, ctx->stream));
   rl::SolveParams& P = ctx->sp;
   memset(&P, 0, sizeof(P));
   P.N = N; P.B = (int)B; P.K = in->K;
@@ -285,9 +308,17 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
     (void)capacity;
     ctx->coop = e ? (e[0] == '1') : (n > 6);
   }
+  if (ctx->spec_G) {  // the speculative kernel writes x, l, L in host layout itself
+    ctx->coop = false;
+    ctx->cost_id = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
+    CU(ctx->d_out1.reserve((size_t)n * (N + 1) * B * 8));
+    CU(ctx->d_out2.reserve((size_t)m * N * B * 8));
+    CU(ctx->d_out3.reserve((size_t)m * n * N * B * 8));
+    P.xo = ctx->d_out1.as<double>(); P.lo = ctx->d_out2.as<double>(); P.Lo = ctx->d_out3.as<double>();
+  }
   ctx->dynamic = false;
-  ctx->traj_retained = false;
-  if (!ctx->coop) {
+  ctx->traj_retained = ctx->spec_G > 0;
+  if (!ctx->coop && !ctx->spec_G) {
     // Lane-level refill (persistent kernel pulling instances from a queue) is an opt-in experiment: measured
     // SLOWER than the static theta-sorted assignment (148 vs 120 ms on the bench fleet, profiles/r01_dynamic_refill_ab.jsonl)
     // because refilled lanes fall out of phase with their warp and most trips then carry a partially used optimising pass.
@@ -326,6 +357,11 @@ static int run_internal(ratilqr_ctx* ctx, int reps, float* ms_total) {
     if (ctx->coop) {
       if (rll::launch_solve_coop(ctx->model_id, ctx->coop_cost_id, ctx->sp, ctx->d_coop_traj.as<double>(), ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
       if (int rc = check_launch(ctx, "k_ileqg_solve_coop")) return rc;
+      continue;
+    }
+    if (ctx->spec_G) {
+      if (rll::launch_solve_spec(ctx->model_id, ctx->cost_id, ctx->spec_G, ctx->sp, ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
+      if (int rc = check_launch(ctx, "k_ileqg_solve_spec")) return rc;
       continue;
     }
     if (ctx->dynamic) CU(cudaMemsetAsync(ctx->sp.queue, 0, 4, ctx->stream));

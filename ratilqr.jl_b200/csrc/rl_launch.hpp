@@ -17,6 +17,11 @@ int launch_solve(int model_id, int cost_id, const rl::SolveParams& P, cudaStream
 int coop_smem_query(int model_id, int cost_id, int N, size_t* smem_bytes);
 int launch_solve_coop(int model_id, int cost_id, const rl::SolveParams& P, double* traj_global, cudaStream_t st);
 
+// speculative latency kernel for small batches (rl_spec.cuh): G = 2, 4 or 8 lanes per instance; the workspace holds one
+// column per LANE (B * G columns) with double-buffered Lg / DL; x, l, L are written in host layout to P.xo / lo / Lo
+bool spec_supported(int model_id, int cost_id);
+int launch_solve_spec(int model_id, int cost_id, int G, const rl::SolveParams& P, cudaStream_t st);
+
 // SoA workspace -> host-layout outputs (x, l, L), tile transpose through shared memory
 void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg, const int32_t* cur,
                    const int32_t* perm, double* x_out, double* l_out, double* L_out, cudaStream_t st);

@@ -9,6 +9,7 @@
 
 #include "../../ratilqr.jl_b200/csrc/rl_components.cuh"
 #include "../../ratilqr.jl_b200/csrc/rl_coop.cuh"
+#include "../../ratilqr.jl_b200/csrc/rl_spec.cuh"
 #include "../../ratilqr.jl_b200/csrc/rl_host.hpp"
 
 #include "../../ratilqr.jl_b200/csrc/rl_user.cuh"
@@ -109,10 +110,38 @@ static void ric(int N, int B, int optimise, const double* q, const double* qv, c
 
 static int g_dynamic = 0;  // 1: emulate the opt-in persistent kernel with lane-level refill (RATILQR_DYNAMIC=1)
 static int g_coop = 0;  // 1: emulate the warp-cooperative kernel (32 virtual lanes run phase by phase)
+static int g_spec = 0;  // 2 / 4 / 8: emulate the speculative latency kernel with this many lanes per instance (rl_spec.cuh)
+
+// the speculative kernel on the host: the G lanes of a group run their round one after another, then the decision is
+// replayed once (on the device every lane replays it on shuffled copies of the same results)
+template <class D, class CT, int G>
+static void run_spec(const SolveParams& P, size_t B) {
+  double stage_area[2 * RL_STAGE_NV];
+  Stage sg; sg.base = stage_area; sg.stride = 1;
+  for (size_t slot = 0; slot < B; ++slot) {
+    const size_t inst = P.perm ? (size_t)P.perm[slot] : slot;
+    const size_t p = inst / (size_t)P.K;
+    if (P.active && !P.active[p]) continue;
+    const double* cp = P.cost_params + (P.cp_count > 1 ? p * (size_t)P.ncp : 0);
+    const double theta = P.theta[inst];
+    const size_t t0 = slot * G;  // first thread of the group
+    SpecCols C;
+    C.P = &P; C.tile = t0 >> 5; C.lane0 = t0 & 31; C.n = D::n; C.m = D::m; C.N = P.N;
+    SpecState S;
+    spec_state_init(P, S);
+    while (!S.done) {
+      SpecLaneRes res[G];
+      for (int g = 0; g < G; ++g) res[g] = spec_lane_work<D, CT>(P, C, g, S, cp, theta, p, sg);
+      spec_decide<G>(P, S, res, inst, true);
+    }
+    for (int g = 0; g < G; ++g) spec_write_outputs(P, C, S, inst, g, G);
+  }
+}
 
 extern "C" {
 
 int32_t hostemu_set_coop(int32_t v) { g_coop = v; return 0; }
+int32_t hostemu_set_spec(int32_t v) { g_spec = (v == 2 || v == 4 || v == 8) ? v : 0; return 0; }
 int32_t hostemu_set_dynamic(int32_t v) { g_dynamic = v; return 0; }
 
 int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
@@ -122,9 +151,11 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
   const size_t B = (size_t)in->P * in->K;
   rlh::WPrep wp;
   if (!rlh::prep_W(n, N, desc->W, desc->W_time_varying, wp)) return -2;
-  const size_t Bp = (B + 31) / 32 * 32;  // warp-tiled workspace
-  std::vector<double> X(2 * (size_t)(N + 1) * n * Bp), U(2 * (size_t)N * m * Bp), Lg((size_t)N * m * n * Bp, 0.0),
-      DL((size_t)N * m * Bp), value(B), mu(B), dcur(B), eps;
+  const bool spec = g_spec && !g_coop && !g_dynamic && n <= 6 && desc->model_id < 1000 && desc->cost_id < 100;
+  const size_t cols = spec ? B * g_spec : B, pol = spec ? 2 : 1;
+  const size_t Bp = (cols + 31) / 32 * 32;  // warp-tiled workspace
+  std::vector<double> X(2 * (size_t)(N + 1) * n * Bp), U(2 * (size_t)N * m * Bp), Lg(pol * (size_t)N * m * n * Bp, 0.0),
+      DL(pol * (size_t)N * m * Bp), value(B), mu(B), dcur(B), eps;
   std::vector<int32_t> status(B), iters(B), trials(B), restarts(B), cur(B);
   int cap = out->eps_hist ? out->eps_hist_cap : 0;
   eps.assign(B * cap * 2 + 2, 0.0);
@@ -150,6 +181,35 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
   }
   P.perm = in->K >= 2 ? perm.data() : nullptr;
   const int cost_id = (desc->model_id < 1000 && rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_QUADROTOR && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
+  if (spec) {
+    std::vector<double> xo((size_t)n * (N + 1) * B), lo((size_t)m * N * B), Lo((size_t)m * n * N * B, 0.0);
+    P.xo = xo.data(); P.lo = lo.data(); P.Lo = Lo.data();
+    const int cid = (rlh::quad_is_diag(desc) && desc->model_id != RATILQR_MODEL_POWER_LAW) ? RL_COST_QUAD_DIAG : desc->cost_id;
+    int rc2 = dispatch(desc->model_id, cid, [&](auto D, auto CT) {
+      using DD = decltype(D);
+      using CC = decltype(CT);
+      if constexpr (DD::n <= 6) {
+        if (g_spec == 8) run_spec<DD, CC, 8>(P, B);
+        else if (g_spec == 4) run_spec<DD, CC, 4>(P, B);
+        else run_spec<DD, CC, 2>(P, B);
+      }
+    });
+    if (rc2) return rc2;
+    for (size_t b = 0; b < B; ++b) {
+      if (out->value) out->value[b] = value[b];
+      if (out->status) out->status[b] = status[b];
+      if (out->iters) out->iters[b] = iters[b];
+      if (out->trials) out->trials[b] = trials[b];
+      if (out->restarts) out->restarts[b] = restarts[b];
+      if (out->mu) out->mu[b] = mu[b];
+      if (out->d_current) out->d_current[b] = dcur[b];
+    }
+    if (out->x) memcpy(out->x, xo.data(), xo.size() * 8);
+    if (out->l) memcpy(out->l, lo.data(), lo.size() * 8);
+    if (out->L) memcpy(out->L, Lo.data(), Lo.size() * 8);
+    if (cap) memcpy(out->eps_hist, eps.data(), B * cap * 16);
+    return 0;
+  }
   if (g_coop) {
     std::vector<double> xo((size_t)n * (N + 1) * B), lo((size_t)m * N * B), Lo((size_t)m * n * N * B, 0.0);
     P.perm = nullptr; P.xo = xo.data(); P.lo = lo.data(); P.Lo = Lo.data();
