@@ -154,7 +154,8 @@ def test_c5_fleet_64_problems_T50_ce_defaults(gpu_be, oracle_be):
     opts = make_opts()
     uflat = np.ascontiguousarray(u.ravel(order="F"))
     for p in range(P):
-        d = prob.spec(cost_params=cps[p]).desc()
+        sp = prob.spec(cost_params=cps[p])  # keep alive: desc() points into its arrays
+        d = sp.desc()
         ce = OracleCEOpts(1.0, 2.0, 10, 3, 5, 0.5, 0)
         outs = [C.c_double() for _ in range(6)]
         nz, st = C.c_int64(), C.c_int32()
@@ -174,7 +175,6 @@ def test_c5_fleet_64_problems_T50_ce_defaults(gpu_be, oracle_be):
         if p < 4:
             rng = np.random.Generator(np.random.Philox(key=256 + p))
             w = np.einsum("ij,jks->iks", np.linalg.cholesky(prob.W(0)), rng.standard_normal((4, 50, 256)))
-            sp = prob.spec(cost_params=cps[p])
             gm = gpu_be.mc_rollout(sp, x, l, L, 256, noise=w, theta_risk=1.0)
             om = oracle_be.mc_rollout(sp, x, l, L, 256, noise=w, theta_risk=1.0)
             assert relerr(gm["J"], om["J"]) < 1e-9 and relerr(gm["stats"], om["stats"]) < 1e-9
