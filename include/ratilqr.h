@@ -163,6 +163,18 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
                                double* mu, double* sigma, int64_t* nz_used, int32_t* rounds,
                                ratilqr_ileqg_out* final);
 
+/* The same solve! for ONE problem -- the reference's own call shape (cross_entropy_bilevel_optimization.jl:364-367):
+ * x0 n, u_init m*N, scalars in / out; whole CE loop on the device incl. the elite selection over the theta population
+ * (one CTA ranks a population of up to thousands of samples, e.g. configs[1]'s 1024).  Equivalent to the fleet call
+ * with P = 1. */
+int32_t ratilqr_ce_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                         const ratilqr_ce_opts* ce, const double* x0, const double* u_init, double kl_bound,
+                         const double* z_inject, int64_t nz, uint64_t seed,
+                         double* mu_init, double* sigma_init,
+                         double* theta_opt, double* value, double* theta_min, double* theta_max,
+                         double* mu, double* sigma, int64_t* nz_used, int32_t* rounds,
+                         ratilqr_ileqg_out* final);
+
 /* solve!(::NelderMeadBilevelOptimizationSolver, ...) (nelder_mead_bilevel_optimization.jl:276-352) for a fleet of P
  * independent problems in lock-step rounds.  Evaluations are pure functions of theta, so every round solves, in ONE
  * batched launch, all candidates the decision tree of step! (:174-252) can ask for (theta_r, theta_e, both possible
@@ -178,6 +190,13 @@ int32_t ratilqr_nm_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
                                double* theta_high_init, double* theta_low_init, double* c_high, double* c_low,
                                int32_t* has_c, double* theta_opt, double* value, int32_t* nm_iters, int32_t* n_evals,
                                ratilqr_ileqg_out* final);
+
+/* The same solve! for ONE problem (nelder_mead_bilevel_optimization.jl:276-279); has_c: 2 flags (c_high, c_low known). */
+int32_t ratilqr_nm_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                         const ratilqr_nm_opts* nm, const double* x0, const double* u_init, double kl_bound,
+                         double* theta_high_init, double* theta_low_init, double* c_high, double* c_low,
+                         int32_t* has_c, double* theta_opt, double* value, int32_t* nm_iters, int32_t* n_evals,
+                         ratilqr_ileqg_out* final);
 
 /* Device-resident variant used for throughput measurement: stage once, run many times.
  * stage = H2D of inputs; run = the solve kernel only, `reps` launches back to back on the

@@ -188,6 +188,12 @@ class CApi:
                                                       ip, OUT])
         self.f_nm_fleet = self._fn("nm_solve_fleet", [vp, PD, IO, C.POINTER(NmOpts), i32, dp, i32, dp, i32, f64, dp, dp, dp, dp, ip,
                                                       dp, dp, ip, ip, OUT])
+        # (the oracle exports oracle_ce_solve / oracle_nm_solve with its OWN, older argument lists -- the tests call those
+        #  directly -- so the single-problem entry points are bound for the product library only)
+        one = (lambda name, at: self._fn(name, at)) if self.needs_ctx else (lambda name, at: self._fn("__absent__" + name, at))
+        self.f_ce_one = one("ce_solve", [vp, PD, IO, C.POINTER(CeOpts), dp, dp, f64, dp, C.c_int64, C.c_uint64, dp, dp, dp, dp,
+                                              dp, dp, dp, dp, C.POINTER(C.c_int64), C.POINTER(i32), OUT])
+        self.f_nm_one = one("nm_solve", [vp, PD, IO, C.POINTER(NmOpts), dp, dp, f64, dp, dp, dp, dp, ip, dp, dp, ip, ip, OUT])
         self.f_stage = self._fn("ileqg_stage", [vp, PD, IO, BI])
         self.f_run = self._fn("ileqg_run", [vp, i32, C.POINTER(C.c_float)])
         self.f_fetch = self._fn("ileqg_fetch", [vp, OUT])
@@ -337,6 +343,55 @@ class CApi:
                                     C.byref(out)), "ce_solve_fleet")
         res["mu_init"], res["sigma_init"], res["rounds"] = mu_i, sg_i, int(rounds.value)
         return res
+
+    def ce_solve(self, spec, x0, u_init, kl_bound, mu_init, sigma_init, num_samples=10, num_elite=3, iter_max=5, lam=0.5,
+                 use_theta_max=False, z_inject=None, seed=0, opts=None):
+        """solve!(::CrossEntropyBilevelOptimizationSolver) for ONE problem, whole loop on the device (ratilqr_ce_solve)."""
+        opts = opts or make_opts()
+        n, m, N = spec.n, spec.m, spec.N
+        x0f, uf = _f64(x0), _f64(u_init)
+        zf, nz = None, 0
+        if z_inject is not None:
+            zf = np.ascontiguousarray(np.asarray(z_inject, dtype=np.float64).ravel())
+            nz = zf.size
+        sc = {k: np.zeros(1) for k in ("theta_opt", "value", "theta_min", "theta_max", "mu", "sigma")}
+        mu_i, sg_i = np.array([float(mu_init)]), np.array([float(sigma_init)])
+        nzu, st, it = np.zeros(1, np.int64), np.zeros(1, np.int32), np.zeros(1, np.int32)
+        x, l, L = np.zeros((n, N + 1), order="F"), np.zeros((m, N), order="F"), np.zeros((m, n, N), order="F")
+        out = IleqgOut(_dp(x), _dp(l), _dp(L), None, _ip(st), _ip(it), None, None, None, None, None, 0)
+        ce = CeOpts(int(num_samples), int(num_elite), int(iter_max), float(lam), int(bool(use_theta_max)))
+        rounds = C.c_int32(0)
+        d = spec.desc()
+        self._check(self.f_ce_one(self.ctx, C.byref(d), C.byref(opts), C.byref(ce), _dp(x0f), _dp(uf), float(kl_bound), _dp(zf), nz,
+                                  int(seed), _dp(mu_i), _dp(sg_i), _dp(sc["theta_opt"]), _dp(sc["value"]), _dp(sc["theta_min"]),
+                                  _dp(sc["theta_max"]), _dp(sc["mu"]), _dp(sc["sigma"]), nzu.ctypes.data_as(C.POINTER(C.c_int64)),
+                                  C.byref(rounds), C.byref(out)), "ce_solve")
+        res = {k: float(v[0]) for k, v in sc.items()}
+        res.update(mu_init=float(mu_i[0]), sigma_init=float(sg_i[0]), nz_used=int(nzu[0]), rounds=int(rounds.value),
+                   status=int(st[0]), iters=int(it[0]), x=x, l=l, L=L)
+        return res
+
+    def nm_solve(self, spec, x0, u_init, kl_bound, state=None, alpha=1.0, beta=2.0, gamma=0.5, eps=1e-2, lam=0.5, iter_max=100,
+                 theta_high_init=3.0, theta_low_init=1e-8, opts=None):
+        """solve!(::NelderMeadBilevelOptimizationSolver) for ONE problem, whole loop on the device (ratilqr_nm_solve)."""
+        opts = opts or make_opts()
+        n, m, N = spec.n, spec.m, spec.N
+        x0f, uf = _f64(x0), _f64(u_init)
+        if state is None:
+            state = dict(theta_high_init=np.array([float(theta_high_init)]), theta_low_init=np.array([float(theta_low_init)]),
+                         c_high=np.zeros(1), c_low=np.zeros(1), has_c=np.zeros(2, np.int32))
+        stt = {k: np.ascontiguousarray(v).copy() for k, v in state.items()}
+        th, val = np.zeros(1), np.zeros(1)
+        it, ev, st = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32)
+        x, l, L = np.zeros((n, N + 1), order="F"), np.zeros((m, N), order="F"), np.zeros((m, n, N), order="F")
+        out = IleqgOut(_dp(x), _dp(l), _dp(L), None, _ip(st), None, None, None, None, None, None, 0)
+        nm = NmOpts(alpha, beta, gamma, eps, lam, int(iter_max))
+        d = spec.desc()
+        self._check(self.f_nm_one(self.ctx, C.byref(d), C.byref(opts), C.byref(nm), _dp(x0f), _dp(uf), float(kl_bound),
+                                  _dp(stt["theta_high_init"]), _dp(stt["theta_low_init"]), _dp(stt["c_high"]), _dp(stt["c_low"]),
+                                  _ip(stt["has_c"]), _dp(th), _dp(val), _ip(it), _ip(ev), C.byref(out)), "nm_solve")
+        return dict(theta_opt=float(th[0]), value=float(val[0]), nm_iters=int(it[0]), n_evals=int(ev[0]), status=int(st[0]),
+                    x=x, l=l, L=L, state=stt)
 
     def nm_solve_fleet(self, spec, x0, u_init, kl_bound, state=None, alpha=1.0, beta=2.0, gamma=0.5, eps=1e-2, lam=0.5,
                        iter_max=100, theta_high_init=3.0, theta_low_init=1e-8, opts=None, want=("x", "l", "L")):

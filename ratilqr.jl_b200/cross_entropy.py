@@ -164,6 +164,42 @@ def solve_(ce, problem, x_0, u_array, rng, verbose=False, serial=False, **kw):
                 raise
 
 
+def solve_on_device_(ce, problem, x_0, u_array, rng, verbose=False, **kw):
+    """solve! (:364-415) with the WHOLE CE loop on the device (ratilqr_ce_solve): draws, batched iLEQG solves, feasibility /
+    redraw logic, elite selection and refit, final solve with the retry rule.  The θ draws are the caller's rng stream:
+    standard normals are taken from a copy of `rng` and injected (rand(rng, Normal(μ, σ)) = μ + σ·randn(rng), :235-237), then
+    `rng` is advanced by the number the solve consumed -- the same samples, and the same generator state afterwards, as the
+    host loop solve_().  Returns the reference's 7-tuple and persists μ_init / σ_init in `ce` like the reference (:66-68)."""
+    import copy
+    kl_bound = float(kw["kl_bound"])
+    assert kl_bound >= 0, "KL Divergence Bound must be non-negative"
+    initialize_(ce)
+    spec = problem.spec()
+    opts = ILEQGSolver(problem, **ce.ileqg_kwargs()).opts()
+    nz = max(4096, 64 * ce.num_samples * ce.iter_max)
+    while True:
+        z = copy.deepcopy(rng).standard_normal(nz)
+        try:
+            r = ce._be().ce_solve(spec, np.asarray(x_0, float), np.stack(u_array, axis=-1), kl_bound, ce.mu_init, ce.sigma_init,
+                                  num_samples=ce.num_samples, num_elite=ce.num_elite, iter_max=ce.iter_max, lam=ce.lam,
+                                  use_theta_max=ce.use_theta_max, z_inject=z, opts=opts)
+            break
+        except Exception as e:  # injected stream exhausted by a long redraw phase: retry with a longer one
+            if "exhausted" not in str(e) or nz >= 1 << 24:
+                raise
+            nz *= 4
+    if r["nz_used"]:
+        rng.standard_normal(r["nz_used"])
+    ce.mu_init, ce.sigma_init, ce.mu, ce.sigma = r["mu_init"], r["sigma_init"], r["mu"], r["sigma"]
+    if kl_bound > 0:
+        ce.theta_min, ce.theta_max, ce.iter_current = r["theta_min"], r["theta_max"], ce.iter_max
+    N = problem.N
+    xa = [r["x"][:, k].copy() for k in range(N + 1)]
+    la = [r["l"][:, k].copy() for k in range(N)]
+    La = [r["L"][:, :, k].copy() for k in range(N)]
+    return r["theta_opt"], xa, la, La, r["value"], r["theta_min"], r["theta_max"]
+
+
 def solve_fleet_(ce, problem, x0, u_init, kl_bound, cost_params=None, rng_seed=0, z_inject=None, want=("x", "l", "L")):
     """solve! for a FLEET of independent problems in one call (additive API): x0 (n, P), per-problem cost parameter blocks
     (P, ncp).  The whole CE loop runs on the device (ratilqr_ce_solve_fleet).  Returns a dict of per-problem arrays and

@@ -1077,6 +1077,7 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
     UP(ctx->s[8], lzeros.data(), Pb); UP(ctx->s[9], ones.data(), (size_t)P * 4);  // cursor = 0 ; iter = 1
     UP(ctx->s[10], ones.data(), (size_t)P * 4); UP(ctx->s[11], izeros.data(), (size_t)P * 4);  // active ; err
     CU(ctx->s[12].reserve(8));
+    CU(ctx->s[14].reserve((size_t)P * ce->num_elite * 8));  // elites in rank order (CTA-per-problem refit)
     if (z_inject) { UP(ctx->s[13], z_inject, (size_t)P * nz * 8); c.z = ctx->s[13].as<double>(); }
   } else {
     in.K = 1;
@@ -1104,7 +1105,7 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
       if ((rc = check_launch(ctx, "k_ce_draw"))) return rc;
       if ((rc = run_internal(ctx, 1, nullptr))) return rc;
       CU(cudaMemsetAsync(c.n_active, 0, 4, st));
-      rll::launch_ce_update(c, st);
+      rll::launch_ce_update(c, ctx->s[14].as<double>(), st);
       if ((rc = check_launch(ctx, "k_ce_update"))) return rc;
       int32_t n_active = 0;
       CU(cudaMemcpyAsync(&n_active, c.n_active, 4, cudaMemcpyDeviceToHost, st));
@@ -1243,6 +1244,15 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   return 0;
 }
 
+int32_t ratilqr_ce_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                         const ratilqr_ce_opts* ce, const double* x0, const double* u_init, double kl_bound,
+                         const double* z_inject, int64_t nz, uint64_t seed, double* mu_init, double* sigma_init,
+                         double* theta_opt, double* value, double* theta_min, double* theta_max, double* mu, double* sigma,
+                         int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out) {
+  return ratilqr_ce_solve_fleet(ctx, desc, opts, ce, 1, x0, 1, u_init, 1, kl_bound, z_inject, nz, seed, mu_init, sigma_init,
+                                theta_opt, value, theta_min, theta_max, mu, sigma, nz_used, rounds_out, final_out);
+}
+
 // ---- RAT iLQR++ for a fleet of problems (nelder_mead_bilevel_optimization.jl:276-352) -------------------------------
 int32_t ratilqr_nm_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
                                const ratilqr_nm_opts* nm, int32_t P, const double* x0, int32_t x0_count,
@@ -1317,6 +1327,14 @@ int32_t ratilqr_nm_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   CU(cudaStreamSynchronize(st));
   if (final_out) return fetch_internal(ctx, final_out);
   return 0;
+}
+
+int32_t ratilqr_nm_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                         const ratilqr_nm_opts* nm, const double* x0, const double* u_init, double kl_bound,
+                         double* theta_high_init, double* theta_low_init, double* c_high, double* c_low, int32_t* has_c,
+                         double* theta_opt, double* value, int32_t* nm_iters, int32_t* n_evals, ratilqr_ileqg_out* final_out) {
+  return ratilqr_nm_solve_fleet(ctx, desc, opts, nm, 1, x0, 1, u_init, 1, kl_bound, theta_high_init, theta_low_init, c_high,
+                                c_low, has_c, theta_opt, value, nm_iters, n_evals, final_out);
 }
 
 int32_t ratilqr_fp64_peak_probe(ratilqr_ctx* ctx, double* tflops, float* ms) {

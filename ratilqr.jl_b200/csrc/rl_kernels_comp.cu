@@ -275,6 +275,118 @@ __global__ void k_ce_update(CeFleet c) {
   else { c.iter[p] += 1; atomicAdd(c.n_active, 1); }
 }
 
+// ---- the same two steps for a LARGE theta population (configs[1]: one problem x 1024 theta): one CTA per problem ------
+// k_ce_draw_cta: candidate t_i = mu + sigma z_i is a pure function of the stream position i, so a chunk of candidates is
+// evaluated in parallel and the positive ones are compacted in stream order by a block-wide prefix sum -- exactly the
+// samples, in the order, that the sequential rejection loop of get_positive_samples (:233-246) keeps.
+constexpr int CE_CTA = 256;
+__global__ void __launch_bounds__(CE_CTA) k_ce_draw_cta(CeFleet c) {
+  const int p = blockIdx.x;
+  if (!c.active[p]) return;
+  __shared__ int wsum[CE_CTA / 32];
+  __shared__ int s_cnt, s_stop;
+  __shared__ long long s_cur;
+  const bool first = c.iter[p] == 1;
+  const double mm = first ? c.mu_init[p] : c.mu[p], ss = first ? c.sigma_init[p] : c.sigma[p];
+  if (threadIdx.x == 0) { s_cnt = 0; s_cur = c.cursor[p]; s_stop = 0; }
+  __syncthreads();
+  long long guard = 0;
+  while (true) {
+    const long long base = s_cur;
+    const int cnt0 = s_cnt;
+    const long long i = base + threadIdx.x;
+    bool in_range = !(c.z && i >= c.nz);
+    double t = -1.0;
+    if (in_range) {
+      double z0, z1;
+      if (c.z) z0 = c.z[(size_t)p * c.nz + i];
+      else rl::philox_normal2(c.seed, (uint64_t)(c.p0 + p), (uint32_t)i, (uint32_t)(i >> 32), &z0, &z1);
+      t = mm + ss * z0;
+    }
+    const bool pos = in_range && t > 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, pos);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    int before = __popc(bal & ((1u << lane) - 1));
+    for (int k = 0; k < w; ++k) before += wsum[k];
+    const int slot = cnt0 + before;
+    if (pos && slot < c.S) c.theta[(size_t)p * c.S + slot] = t;
+    if (pos && slot == c.S - 1) { s_cur = i + 1; s_stop = 1; }  // the S-th positive sample: the stream stops right after it
+    __syncthreads();
+    if (threadIdx.x == 0 && !s_stop) {
+      int tot = 0;
+      for (int k = 0; k < CE_CTA / 32; ++k) tot += wsum[k];
+      s_cnt = cnt0 + tot;
+      s_cur = base + CE_CTA;
+      guard += CE_CTA;
+      if ((c.z && s_cur >= c.nz) || guard > 1000000) { c.err[p] = 1; c.active[p] = 0; s_stop = 2; }  // stream exhausted
+    }
+    __syncthreads();
+    if (s_stop) break;
+  }
+  if (threadIdx.x == 0) c.cursor[p] = s_cur;
+}
+
+// k_ce_update_cta: step! :291-334 with the O(S^2) stable rank computed by the whole CTA; the elite mean / std are summed
+// by one thread in rank order, i.e. in the order the reference's sorted array is summed.
+__global__ void __launch_bounds__(CE_CTA) k_ce_update_cta(CeFleet c, double* elite_ws) {
+  const int p = blockIdx.x;
+  if (!c.active[p]) return;
+  const int S = c.S;
+  const double* th = c.theta + (size_t)p * S;
+  const double* val = c.value + (size_t)p * S;
+  const int32_t* st = c.status + (size_t)p * S;
+  double* elite = elite_ws + (size_t)p * c.num_elite;
+  auto cost = [&](int i) { return st[i] == 0 ? val[i] + c.kl / th[i] : HUGE_VAL; };
+  __shared__ int s_inf, s_go;
+  if (threadIdx.x == 0) { s_inf = 0; s_go = 0; }
+  __syncthreads();
+  int ninf = 0;
+  for (int i = threadIdx.x; i < S; i += CE_CTA) { double ci = cost(i); ninf += (ci == HUGE_VAL || ci == -HUGE_VAL) ? 1 : 0; }
+  if (ninf) atomicAdd(&s_inf, ninf);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int num_valid = S - s_inf;
+    const double thr = fmax((double)c.num_elite, S * c.lambda);
+    const bool first = c.iter[p] == 1;
+    if (first && num_valid < thr) { c.mu_init[p] *= c.lambda; c.sigma_init[p] *= c.lambda; atomicAdd(c.n_active, 1); }
+    else if (first && num_valid == S) { c.mu_init[p] /= c.lambda; c.sigma_init[p] /= c.lambda; s_go = 1; }
+    else if (!(num_valid >= thr)) atomicAdd(c.n_active, 1);
+    else s_go = 1;
+    if (s_go) {  // :314-324, sequential because of the if / elseif quirk
+      double tmin = c.theta_min[p], tmax = c.theta_max[p];
+      for (int i = 0; i < S; ++i) {
+        double ci = cost(i);
+        if (ci == HUGE_VAL || ci == -HUGE_VAL) continue;
+        if (th[i] < tmin) tmin = th[i];
+        else if (th[i] > tmax) tmax = th[i];
+      }
+      c.theta_min[p] = tmin; c.theta_max[p] = tmax;
+    }
+  }
+  __syncthreads();
+  if (!s_go) return;
+  for (int i = threadIdx.x; i < S; i += CE_CTA) {
+    const double ci = cost(i);
+    int rank = 0;
+    for (int j = 0; j < S; ++j) rank += key_less(cost(j), j, ci, i) ? 1 : 0;
+    if (rank < c.num_elite) elite[rank] = th[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    for (int e = 0; e < c.num_elite; ++e) sum += elite[e];
+    const double mu_new = sum / c.num_elite;  // :329
+    double ss = 0.0;
+    for (int e = 0; e < c.num_elite; ++e) ss += (elite[e] - mu_new) * (elite[e] - mu_new);
+    c.mu[p] = mu_new;
+    c.sigma[p] = sqrt(ss / c.num_elite);  // :330 population std
+    if (c.iter[p] >= c.iter_max) c.active[p] = 0;
+    else { c.iter[p] += 1; atomicAdd(c.n_active, 1); }
+  }
+}
+
 __global__ void k_ce_pick_theta(CeFleet c, double* theta_final) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= c.P) return;
@@ -400,8 +512,15 @@ void launch_nm_final(const NmFleet& c, double* tf, const double* v, const int32_
   k_nm_final<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c, tf, v, s, stage);
 }
 
-void launch_ce_draw(const CeFleet& c, cudaStream_t st) { k_ce_draw<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c); }
-void launch_ce_update(const CeFleet& c, cudaStream_t st) { k_ce_update<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c); }
+// thread per problem for the reference's small populations (10 theta), CTA per problem beyond 32 samples
+void launch_ce_draw(const CeFleet& c, cudaStream_t st) {
+  if (c.S > 32) k_ce_draw_cta<<<c.P, CE_CTA, 0, st>>>(c);
+  else k_ce_draw<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c);
+}
+void launch_ce_update(const CeFleet& c, double* elite_ws, cudaStream_t st) {
+  if (c.S > 32) k_ce_update_cta<<<c.P, CE_CTA, 0, st>>>(c, elite_ws);
+  else k_ce_update<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c);
+}
 void launch_ce_pick_theta(const CeFleet& c, double* tf, cudaStream_t st) { k_ce_pick_theta<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c, tf); }
 void launch_ce_final_update(const CeFleet& c, double* tf, const double* v, const int32_t* s, cudaStream_t st) {
   k_ce_final_update<<<RL_BLOCKS(c.P, 64), 64, 0, st>>>(c, tf, v, s);

@@ -63,19 +63,10 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
   using CT = Cost<CID, D::n, D::m>;
   if constexpr (MID == RATILQR_MODEL_UNICYCLE && CID == RL_COST_QUAD_DIAG) {
     switch (shape_override()) {
+      // (the other shapes of the round-1 sweeps -- 64x{5,7,8}, 32x{8..20} -- lost everywhere and were removed: profiles/r01_tune_*.jsonl)
       case 0: launch_shape<D, CT, 64, 4>(P, st); return;    // 255 regs,  8 warps/SM
       case 1: launch_shape<D, CT, 64, 6>(P, st); return;    // 168 regs, 12 warps/SM
-      case 2: launch_shape<D, CT, 64, 8>(P, st); return;    // 128 regs, 16 warps/SM
-      case 3: launch_shape<D, CT, 32, 8>(P, st); return;    // 255 regs, warp-sized CTAs
-      case 4: launch_shape<D, CT, 32, 12>(P, st); return;   // 168 regs
-      case 5: launch_shape<D, CT, 32, 16>(P, st); return;   // 128 regs
-      case 6: launch_shape<D, CT, 32, 20>(P, st); return;   // 96 regs, 20 warps/SM
-      case 7: launch_shape<D, CT, 32, 14>(P, st); return;   // 144 regs
-      case 8: launch_shape<D, CT, 32, 13>(P, st); return;   // 152 regs
-      case 9: launch_shape<D, CT, 32, 10>(P, st); return;   // 200 regs
-      case 10: launch_shape<D, CT, 64, 7>(P, st); return;   // 144 regs, 14 warps/SM
       case 11: launch_shape<D, CT, 128, 3>(P, st); return;  // 168 regs, 128-thread CTAs
-      case 12: launch_shape<D, CT, 64, 5>(P, st); return;   // 200 regs, 10 warps/SM
       default: {
         // Throughput shape (168 registers, 12 warps/SM) once the batch exceeds what it keeps resident at a time; below
         // that every instance is resident anyway and the 255-register build wins on latency (fewer spills, more ILP per

@@ -76,7 +76,7 @@ struct CeFleet {
   int32_t* n_active;        // single counter
 };
 void launch_ce_draw(const CeFleet& c, cudaStream_t st);
-void launch_ce_update(const CeFleet& c, cudaStream_t st);
+void launch_ce_update(const CeFleet& c, double* elite_ws /* P * num_elite doubles */, cudaStream_t st);
 void launch_ce_pick_theta(const CeFleet& c, double* theta_final, cudaStream_t st);
 void launch_ce_final_update(const CeFleet& c, double* theta_final, const double* value, const int32_t* status, cudaStream_t st);
 
