@@ -70,6 +70,17 @@ enum {
 
 typedef struct ratilqr_ctx ratilqr_ctx;
 
+/* "True model" process noise: a Gaussian mixture  sum_c weights[c] N(means[:,c], covs[:,:,c])
+ * -- the accurate GMM of the reference's generative example, selected there by
+ * f_stochastic(x, u, rng, use_true_model=true) (src/optimal_control_problems.jl:85-86,
+ * 102-115), against the single Gaussian the planner assumes. */
+typedef struct {
+  int32_t n_components;   /* >= 1 */
+  const double* weights;  /* n_components, > 0 (normalised by the library) */
+  const double* means;    /* n * n_components, column-major */
+  const double* covs;     /* n*n * n_components, each positive definite */
+} ratilqr_noise_mixture;
+
 /* f, c, h, W, N of FiniteHorizonRiskSensitiveOptimalControlProblem
  * (optimal_control_problems.jl:67-73), restricted to registered models. */
 typedef struct {
@@ -162,6 +173,32 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
                                double* theta_opt, double* value, double* theta_min, double* theta_max,
                                double* mu, double* sigma, int64_t* nz_used, int32_t* rounds,
                                ratilqr_ileqg_out* final);
+
+/* Receding-horizon RAT iLQR for a fleet of P independent systems, `steps` MPC steps WITHOUT leaving the device -- the
+ * caller the reference does not ship (its solve! is one planning step).  Per step and problem:
+ * plan with solve!(::CrossEntropyBilevelOptimizationSolver) from the current state, warm-started with the shifted
+ * previous plan (ratilqr_ce_solve_fleet's on-device loop); apply the first nominal control to the TRUE system
+ * x+ = f(x, l_0) + w; shift the plan (last control repeated).  States, plans and disturbances never visit the host;
+ * mu_init / sigma_init (P, in-out) persist across the steps and the call exactly like the fields of the reference's solver
+ * struct (cross_entropy_bilevel_optimization.jl:66-68, 297-301).
+ * Disturbance w: `noise` (n*steps*P injected: w of problem p at step t is noise[(p*steps + t)*n ...]) or NULL ->
+ * Philox(noise_seed) drawn from N(0, W) or, when true_noise != NULL, from the true-model Gaussian mixture.
+ * z_inject: steps * P * nz standard normals for the theta draws (step slowest, then problem) or NULL -> Philox(seed + t).
+ * Outputs (problem slowest): x_traj n*(steps+1)*P, u_traj m*steps*P, theta_traj / value_traj steps*P (theta_opt and
+ * value + kl/theta_opt of every plan), step_ms steps (host wall time per step, max over the concurrent sub-fleets). */
+typedef struct {
+  int32_t steps;
+  const double* noise;
+  uint64_t noise_seed;
+  const ratilqr_noise_mixture* true_noise;
+} ratilqr_mpc_opts;
+int32_t ratilqr_mpc_fleet_run(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                              const ratilqr_ce_opts* ce, const ratilqr_mpc_opts* mpc, int32_t P, const double* x0,
+                              const double* u_init, int32_t u_count, double kl_bound,
+                              const double* z_inject, int64_t nz, uint64_t seed,
+                              double* mu_init, double* sigma_init,
+                              double* x_traj, double* u_traj, double* theta_traj, double* value_traj,
+                              float* step_ms, int32_t* rounds_total);
 
 /* The same solve! for ONE problem -- the reference's own call shape (cross_entropy_bilevel_optimization.jl:364-367):
  * x0 n, u_init m*N, scalars in / out; whole CE loop on the device incl. the elite selection over the theta population
@@ -258,16 +295,6 @@ int32_t ratilqr_mc_rollout(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, i
                            int32_t n_samples, const double* noise, uint64_t seed,
                            double theta_risk, double* J, double* stats, double* x_out);
 
-/* "True model" process noise: a Gaussian mixture  sum_c weights[c] N(means[:,c], covs[:,:,c])
- * -- the accurate GMM of the reference's generative example, selected there by
- * f_stochastic(x, u, rng, use_true_model=true) (src/optimal_control_problems.jl:85-86,
- * 102-115), against the single Gaussian the planner assumes. */
-typedef struct {
-  int32_t n_components;   /* >= 1 */
-  const double* weights;  /* n_components, > 0 (normalised by the library) */
-  const double* means;    /* n * n_components, column-major */
-  const double* covs;     /* n*n * n_components, each positive definite */
-} ratilqr_noise_mixture;
 /* Closed-loop Monte Carlo evaluation under the TRUE noise model: same as
  * ratilqr_mc_rollout in Philox mode, but w_k is drawn from `true_noise` instead of N(0, W(k)):
  * E[J], Var[J] and the entropic risk of a policy that was optimised under the Gaussian model. */

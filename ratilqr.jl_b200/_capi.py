@@ -70,6 +70,10 @@ class CeOpts(C.Structure):  # ratilqr_ce_opts
                 ("use_theta_max", C.c_int32)]
 
 
+class MpcOpts(C.Structure):  # ratilqr_mpc_opts
+    _fields_ = [("steps", C.c_int32), ("noise", c_double_p), ("noise_seed", C.c_uint64), ("true_noise", C.POINTER(NoiseMixture))]
+
+
 class NmOpts(C.Structure):  # ratilqr_nm_opts
     _fields_ = [("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double), ("eps", C.c_double), ("lam", C.c_double),
                 ("iter_max", C.c_int32)]
@@ -188,6 +192,8 @@ class CApi:
                                                       ip, OUT])
         self.f_nm_fleet = self._fn("nm_solve_fleet", [vp, PD, IO, C.POINTER(NmOpts), i32, dp, i32, dp, i32, f64, dp, dp, dp, dp, ip,
                                                       dp, dp, ip, ip, OUT])
+        self.f_mpc = self._fn("mpc_fleet_run", [vp, PD, IO, C.POINTER(CeOpts), C.POINTER(MpcOpts), i32, dp, dp, i32, f64, dp, C.c_int64,
+                                                C.c_uint64, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_float), C.POINTER(i32)])
         # (the oracle exports oracle_ce_solve / oracle_nm_solve with its OWN, older argument lists -- the tests call those
         #  directly -- so the single-problem entry points are bound for the product library only)
         one = (lambda name, at: self._fn(name, at)) if self.needs_ctx else (lambda name, at: self._fn("__absent__" + name, at))
@@ -370,6 +376,43 @@ class CApi:
         res.update(mu_init=float(mu_i[0]), sigma_init=float(sg_i[0]), nz_used=int(nzu[0]), rounds=int(rounds.value),
                    status=int(st[0]), iters=int(it[0]), x=x, l=l, L=L)
         return res
+
+    def mpc_fleet_run(self, spec, x0, u_init, steps, kl_bound, mu_init, sigma_init, num_samples=10, num_elite=3, iter_max=5,
+                      lam=0.5, use_theta_max=False, z_inject=None, seed=0, noise=None, noise_seed=0, true_mixture=None, opts=None):
+        """Receding-horizon RAT iLQR for a fleet, `steps` MPC steps on the device (ratilqr_mpc_fleet_run).
+        x0 (n, P); u_init (m, N) or (m, N, P); noise (n, steps, P) injected disturbances or None -> Philox;
+        z_inject (steps, P, nz) standard normals for the theta draws or None -> Philox."""
+        opts = opts or make_opts()
+        n, m, N = spec.n, spec.m, spec.N
+        x0 = np.asarray(x0, dtype=np.float64).reshape(n, -1)
+        P = x0.shape[1]
+        u_init = np.asarray(u_init, dtype=np.float64)
+        u_count = 1 if u_init.ndim == 2 else u_init.shape[-1]
+        x0f, uf = _f64(x0), _f64(u_init)
+        mu_i = np.ascontiguousarray(np.broadcast_to(np.asarray(mu_init, np.float64), (P,))).copy()
+        sg_i = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma_init, np.float64), (P,))).copy()
+        zf, nz = None, 0
+        if z_inject is not None:
+            z = np.ascontiguousarray(np.asarray(z_inject, dtype=np.float64).reshape(steps, P, -1))
+            zf, nz = z.reshape(-1), z.shape[2]
+        nf = None if noise is None else _f64(np.asarray(noise, dtype=np.float64).reshape(n, steps, P))
+        keep = None
+        mo = MpcOpts(int(steps), _dp(nf), int(noise_seed), None)
+        if true_mixture is not None:
+            mix, keep = self._mixture(true_mixture)
+            mo.true_noise = C.pointer(mix)
+        ce = CeOpts(int(num_samples), int(num_elite), int(iter_max), float(lam), int(bool(use_theta_max)))
+        xt = np.zeros((n, steps + 1, P), order="F")
+        ut = np.zeros((m, steps, P), order="F")
+        tt, vt = np.zeros((steps, P), order="F"), np.zeros((steps, P), order="F")
+        ms = np.zeros(steps, np.float32)
+        rounds = C.c_int32(0)
+        d = spec.desc()
+        self._check(self.f_mpc(self.ctx, C.byref(d), C.byref(opts), C.byref(ce), C.byref(mo), P, _dp(x0f), _dp(uf), u_count,
+                               float(kl_bound), _dp(zf), nz, int(seed), _dp(mu_i), _dp(sg_i), _dp(xt), _dp(ut), _dp(tt), _dp(vt),
+                               ms.ctypes.data_as(C.POINTER(C.c_float)), C.byref(rounds)), "mpc_fleet_run")
+        del keep
+        return dict(x=xt, u=ut, theta=tt, value=vt, ms=ms.astype(float), mu_init=mu_i, sigma_init=sg_i, rounds=int(rounds.value))
 
     def nm_solve(self, spec, x0, u_init, kl_bound, state=None, alpha=1.0, beta=2.0, gamma=0.5, eps=1e-2, lam=0.5, iter_max=100,
                  theta_high_init=3.0, theta_low_init=1e-8, opts=None):

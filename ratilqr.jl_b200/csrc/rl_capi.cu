@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,6 +70,9 @@ struct ratilqr_ctx {
   DBuf s[16];
   DBuf d_mix[3];  // true-model noise mixture: cumulative weights, means, Cholesky factors
   DBuf d_cost;
+  // receding-horizon driver (ratilqr_mpc_fleet_run): states / warm starts stay in d_x0 / d_u between the steps
+  bool inputs_on_device = false;  // stage_internal: x0 / u_init are already in d_x0 / d_u (one block per problem)
+  DBuf d_mpc[7];                  // x_traj, u_traj, theta_traj, value_traj, noise, cholW, err
 };
 
 #define CU(expr)                                                                          \
@@ -193,7 +197,8 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   if (const char* m = check_desc_ctx(ctx, desc, true, &um)) FAIL(-1, m);
   ctx->staged_user = um;
   if (const char* m = check_opts(opts)) FAIL(-3, m);
-  if (!in || in->P < 1 || in->K < 1 || !in->x0 || !in->u_init || (!in->theta && !device_theta)) FAIL(-1, "bad batch description");
+  const bool dev_in = ctx->inputs_on_device;
+  if (!in || in->P < 1 || in->K < 1 || ((!in->x0 || !in->u_init) && !dev_in) || (!in->theta && !device_theta)) FAIL(-1, "bad batch description");
   if ((in->x0_count != 1 && in->x0_count != in->P) || (in->u_count != 1 && in->u_count != in->P)) FAIL(-1, "x0_count/u_count must be 1 or P");
   if (desc->cost_params_count != 1 && desc->cost_params_count != in->P) FAIL(-1, "cost_params_count must be 1 or P");
   CU(cudaSetDevice(ctx->device));
@@ -206,8 +211,10 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   UP(ctx->d_Winv, wp.Winv.data(), wp.Winv.size() * 8);
   UP(ctx->d_detW, wp.detW.data(), wp.detW.size() * 8);
   UP(ctx->d_cp, desc->cost_params, (size_t)desc->n_cost_params * desc->cost_params_count * 8);
-  UP(ctx->d_x0, in->x0, (size_t)n * in->x0_count * 8);
-  UP(ctx->d_u, in->u_init, (size_t)m * N * in->u_count * 8);
+  if (!dev_in) {
+    UP(ctx->d_x0, in->x0, (size_t)n * in->x0_count * 8);
+    UP(ctx->d_u, in->u_init, (size_t)m * N * in->u_count * 8);
+  }
   if (device_theta) CU(ctx->d_theta.reserve(B * 8));  // theta is produced on the device (fleet CE)
   else UP(ctx->d_theta, in->theta, B * 8);
   // Kernel choice, part 1: a batch that leaves most of the machine idle runs on the speculative latency kernel
@@ -416,6 +423,24 @@ static int resort_slots_by_last_iters(ratilqr_ctx* ctx, int P, int K) {
   return apply_slot_order(ctx, key, P, K);
 }
 
+// device pointer to l_array (m*N*B, host layout) of the staged solve that just ran: the kernels that keep trajectories in
+// host layout have it already, the thread-per-instance kernel's workspace goes through the tile-transpose gather
+static int device_plan(ratilqr_ctx* ctx, const double** plan) {
+  if (!ctx->staged) FAIL(-4, "nothing staged");
+  if (ctx->traj_retained) {
+    if (!ctx->sp.lo) FAIL(-4, "l_array was not retained by this staged solve");
+    *plan = ctx->sp.lo;
+    return 0;
+  }
+  const size_t B = (size_t)ctx->B;
+  CU(ctx->d_out2.reserve((size_t)ctx->m * ctx->N * B * 8));
+  rll::launch_gather(ctx->n, ctx->m, ctx->N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.cur, ctx->sp.perm, nullptr,
+                     ctx->d_out2.as<double>(), nullptr, ctx->stream);
+  if (int rc = check_launch(ctx, "k_gather")) return rc;
+  *plan = ctx->d_out2.as<double>();
+  return 0;
+}
+
 static int fetch_internal(ratilqr_ctx* ctx, ratilqr_ileqg_out* out) {
   if (!ctx->staged) FAIL(-4, "nothing staged");
   if (!out) FAIL(-1, "null out");
@@ -501,6 +526,7 @@ int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
   for (DBuf* b : all) b->release();
   for (DBuf& b : ctx->s) b.release();
   for (DBuf& b : ctx->d_mix) b.release();
+  for (DBuf& b : ctx->d_mpc) b.release();
   ctx->d_order.release(); ctx->d_key.release();
   if (ctx->h_key) cudaFreeHost(ctx->h_key);
   for (rlu::Module* um : ctx->user_models) { rlu::unload(*um); delete um; }
@@ -1045,9 +1071,10 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
                                 const double* u_init, int32_t u_count, double kl_bound, const double* z_inject,
                                 int64_t nz, uint64_t seed, double* mu_init, double* sigma_init, double* theta_opt,
                                 double* value, double* theta_min, double* theta_max, double* mu, double* sigma,
-                                int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out) {
+                                int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out,
+                                rll::MpcArgs* sink = nullptr) {
   if (!ctx) return -1;
-  if (!ce || P < 1 || !mu_init || !sigma_init || !theta_opt || !value) FAIL(-1, "bad arguments");
+  if (!ce || P < 1 || !mu_init || !sigma_init || ((!theta_opt || !value) && !sink)) FAIL(-1, "bad arguments");
   if (!(kl_bound >= 0)) FAIL(-3, "KL Divergence Bound must be non-negative");  // :368
   if (ce->num_samples < 1 || ce->num_elite < 1 || ce->num_elite > ce->num_samples || ce->iter_max < 1) FAIL(-3, "bad CE options");
   const int S = ce->num_samples;
@@ -1123,7 +1150,7 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
   const bool order_final = kl_bound > 0 && sort_fleet && !ctx->coop && P >= 64 && (int)ctx->fleet_key.size() == P;
   // final solve at theta_opt with the retry rule (:390-414); B = P instances, theta on the device
   in.K = 1;
-  const int fwant = final_out ? ((final_out->x ? 1 : 0) | (final_out->l ? 2 : 0) | (final_out->L ? 4 : 0)) : 0;
+  const int fwant = (final_out ? ((final_out->x ? 1 : 0) | (final_out->l ? 2 : 0) | (final_out->L ? 4 : 0)) : 0) | (sink ? 2 : 0);
   if ((rc = stage_internal(ctx, desc, opts, &in, final_out && final_out->eps_hist ? final_out->eps_hist_cap : 0, true, fwant))) return rc;
   rll::launch_ce_pick_theta(c, ctx->d_theta.as<double>(), st);
   if ((rc = check_launch(ctx, "k_ce_pick_theta"))) return rc;
@@ -1142,6 +1169,12 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
     if (++final_rounds > 10000) FAIL(-6, "final solve retry loop does not terminate");
   }
   ctx->sp.active = nullptr;
+  if (sink) {  // receding-horizon driver: true-system step and plan shift on the device, nothing comes back to the host
+    if ((rc = device_plan(ctx, &sink->plan))) return rc;
+    sink->theta_opt = c.theta_opt; sink->value = c.value_out;
+    if (rll::launch_mpc_advance(*sink, st)) FAIL(-5, "this model is not compiled in");
+    if ((rc = check_launch(ctx, "k_mpc_advance"))) return rc;
+  }
   DOWNSYNC(theta_opt, c.theta_opt, Pb); DOWNSYNC(value, c.value_out, Pb);
   DOWNSYNC(mu_init, c.mu_init, Pb); DOWNSYNC(sigma_init, c.sigma_init, Pb);
   DOWNSYNC(mu, c.mu, Pb); DOWNSYNC(sigma, c.sigma, Pb);
@@ -1239,6 +1272,123 @@ int32_t ratilqr_ce_solve_fleet(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
     if (b > 0) ctx->launches += ctx->children[b - 1]->launches, ctx->children[b - 1]->launches = 0;
   }
   if (rounds_out) *rounds_out = rmax;
+  for (int b = 0; b < K; ++b)
+    if (rcs[b]) { if (b > 0) ctx->err = ctx->children[b - 1]->err; return rcs[b]; }
+  return 0;
+}
+
+// ---- receding-horizon RAT iLQR for a fleet, `steps` MPC steps without leaving the device --------------
+// One block of problems: plan (CE loop + final solve, ce_solve_fleet_block with device-resident x / warm start), then
+// k_mpc_advance applies l_0 to the true system, draws the disturbance, shifts the plan.  mu_init / sigma_init persist
+// across the steps like the fields of the reference's solver struct (cross_entropy...jl:66-68, 297-301).
+static int mpc_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                     const ratilqr_ce_opts* ce, int P, long long p0, int Ptot, const double* x0, const double* u_init,
+                     int u_count, double kl_bound, const double* z_inject, int64_t nz, uint64_t seed,
+                     const ratilqr_mpc_opts* mo, double* mu_init, double* sigma_init, double* x_traj, double* u_traj,
+                     double* theta_traj, double* value_traj, float* step_ms, int32_t* rounds_total) {
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = desc->n, m = desc->m, N = desc->N, steps = mo->steps;
+  cudaStream_t st = ctx->stream;
+  rlh::WPrep wp;
+  if (!rlh::prep_W(desc->n, desc->N, desc->W, desc->W_time_varying, wp)) FAIL(-2, "W(k) is not positive definite");
+  // device-resident state: x (n*P) in d_x0, warm start (m*N*P) in d_u
+  UP(ctx->d_x0, x0, n * P * 8);
+  {
+    std::vector<double> u0(m * N * P);
+    for (int p = 0; p < P; ++p) memcpy(u0.data() + (size_t)p * m * N, u_init + (u_count > 1 ? (size_t)p * m * N : 0), m * N * 8);
+    UP(ctx->d_u, u0.data(), u0.size() * 8);
+    CU(cudaStreamSynchronize(st));  // u0 is a stack vector
+  }
+  CU(ctx->d_mpc[0].reserve(n * (steps + 1) * P * 8)); CU(ctx->d_mpc[1].reserve(m * steps * P * 8));
+  CU(ctx->d_mpc[2].reserve(steps * P * 8)); CU(ctx->d_mpc[3].reserve(steps * P * 8));
+  if (mo->noise) UP(ctx->d_mpc[4], mo->noise, n * steps * P * 8);
+  UP(ctx->d_mpc[5], wp.cholW.data(), n * n * 8);
+  CU(ctx->d_mpc[6].reserve(8));
+  CU(cudaMemsetAsync(ctx->d_mpc[6].p, 0, 4, st));
+  CU(cudaMemcpy2DAsync(ctx->d_mpc[0].p, n * (steps + 1) * 8, ctx->d_x0.p, n * 8, n * 8, P, cudaMemcpyDeviceToDevice, st));  // x_traj[:, 0, p] = x0
+  rll::MpcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.model_id = desc->model_id; a.N = desc->N; a.P = P; a.steps = mo->steps; a.p0 = p0;
+  for (int i = 0; i < 8; ++i) a.mp[i] = i < desc->n_model_params ? desc->model_params[i] : 0.0;
+  a.x = ctx->d_x0.as<double>(); a.u_init = ctx->d_u.as<double>();
+  a.noise = mo->noise ? ctx->d_mpc[4].as<double>() : nullptr;
+  a.cholW = ctx->d_mpc[5].as<double>(); a.seed = mo->noise_seed;
+  if (int rc = upload_mixture(ctx, desc->n, mo->true_noise, a.mix)) return rc;
+  a.x_traj = ctx->d_mpc[0].as<double>(); a.u_traj = ctx->d_mpc[1].as<double>();
+  a.theta_traj = ctx->d_mpc[2].as<double>(); a.value_traj = ctx->d_mpc[3].as<double>(); a.err = ctx->d_mpc[6].as<int32_t>();
+  int rounds_sum = 0;
+  for (int t = 0; t < mo->steps; ++t) {
+    const auto t0 = std::chrono::steady_clock::now();
+    a.t = t;
+    ctx->inputs_on_device = true;
+    int rounds = 0;
+    const double* zt = z_inject ? z_inject + ((size_t)t * Ptot + (size_t)p0) * nz : nullptr;
+    int rc = ce_solve_fleet_block(ctx, desc, opts, ce, P, p0, nullptr, P, nullptr, P, kl_bound, zt, nz, seed + (uint64_t)t, mu_init,
+                                  sigma_init, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &rounds, nullptr, &a);
+    ctx->inputs_on_device = false;
+    if (rc) return rc;
+    rounds_sum += rounds;
+    if (step_ms) step_ms[t] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  int32_t err = 0;
+  CU(cudaMemcpyAsync(&err, ctx->d_mpc[6].p, 4, cudaMemcpyDeviceToHost, st));
+  DOWNSYNC(x_traj, ctx->d_mpc[0].p, n * (steps + 1) * P * 8); DOWNSYNC(u_traj, ctx->d_mpc[1].p, m * steps * P * 8);
+  DOWNSYNC(theta_traj, ctx->d_mpc[2].p, steps * P * 8); DOWNSYNC(value_traj, ctx->d_mpc[3].p, steps * P * 8);
+  CU(cudaStreamSynchronize(st));
+  if (rounds_total) *rounds_total = rounds_sum;
+  if (err) FAIL(-7, "the true system left the domain of its model (DomainError) during the receding-horizon run");
+  return 0;
+}
+
+int32_t ratilqr_mpc_fleet_run(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                              const ratilqr_ce_opts* ce, const ratilqr_mpc_opts* mo, int32_t P, const double* x0,
+                              const double* u_init, int32_t u_count, double kl_bound, const double* z_inject, int64_t nz,
+                              uint64_t seed, double* mu_init, double* sigma_init, double* x_traj, double* u_traj,
+                              double* theta_traj, double* value_traj, float* step_ms, int32_t* rounds_total) {
+  if (!ctx) return -1;
+  if (!desc || !ce || !mo || P < 1 || mo->steps < 1 || !x0 || !u_init || !mu_init || !sigma_init) FAIL(-1, "bad arguments");
+  if (u_count != 1 && u_count != P) FAIL(-1, "u_count must be 1 or P");
+  if (desc->cost_params_count != 1 && desc->cost_params_count != P) FAIL(-1, "cost_params_count must be 1 or P");
+  if (desc->model_id >= RATILQR_MODEL_USER_BASE) FAIL(-5, "user models: drive ratilqr_ce_solve_fleet from the host (the true-system step is compiled for registered models)");
+  const int K = std::min(fleet_blocks(ctx, desc, P, ce->num_samples), (int)P);
+  while ((int)ctx->children.size() < K - 1) {
+    ratilqr_ctx* ch = nullptr;
+    if (int rc = ratilqr_create(&ch, ctx->device)) FAIL(rc, "could not create a sub-fleet context");
+    ch->parent = ctx;
+    ctx->children.push_back(ch);
+  }
+  const size_t n = desc->n, m = desc->m, N = desc->N, steps = mo->steps;
+  std::vector<int> rcs(K, 0), rounds(K, 0);
+  std::vector<std::vector<float>> ms(K, std::vector<float>(steps, 0.f));
+  auto run_block = [&](int b) {
+    const long long lo = (long long)P * b / K, hi = (long long)P * (b + 1) / K;
+    const int Pb = (int)(hi - lo);
+    ratilqr_ctx* c = b == 0 ? ctx : ctx->children[b - 1];
+    ratilqr_problem_desc d = *desc;
+    if (desc->cost_params_count == P) { d.cost_params = desc->cost_params + (size_t)lo * desc->n_cost_params; d.cost_params_count = Pb; }
+    ratilqr_mpc_opts mb = *mo;
+    if (mo->noise) mb.noise = mo->noise + n * steps * lo;
+    auto off = [&](double* q, size_t per) { return q ? q + per * lo : nullptr; };
+    rcs[b] = mpc_block(c, &d, opts, ce, Pb, lo, P, x0 + n * lo, u_count == P ? u_init + m * N * lo : u_init, u_count, kl_bound,
+                       z_inject, nz, seed, &mb, mu_init + lo, sigma_init + lo, off(x_traj, n * (steps + 1)), off(u_traj, m * steps),
+                       off(theta_traj, steps), off(value_traj, steps), ms[b].data(), &rounds[b]);
+  };
+  std::vector<std::thread> th;
+  int spawned = 1;
+  try {
+    for (int b = 1; b < K; ++b) { th.emplace_back(run_block, b); ++spawned; }
+  } catch (...) {
+  }
+  run_block(0);
+  for (int b = spawned; b < K; ++b) run_block(b);
+  for (auto& t : th) t.join();
+  int rsum = 0;
+  for (int b = 0; b < K; ++b) {
+    rsum = std::max(rsum, rounds[b]);
+    if (b > 0) ctx->launches += ctx->children[b - 1]->launches, ctx->children[b - 1]->launches = 0;
+  }
+  if (step_ms) for (size_t t = 0; t < steps; ++t) { float mx = 0.f; for (int b = 0; b < K; ++b) mx = std::max(mx, ms[b][t]); step_ms[t] = mx; }
+  if (rounds_total) *rounds_total = rsum;
   for (int b = 0; b < K; ++b)
     if (rcs[b]) { if (b > 0) ctx->err = ctx->children[b - 1]->err; return rcs[b]; }
   return 0;

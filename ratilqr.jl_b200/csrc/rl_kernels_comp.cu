@@ -17,6 +17,44 @@ int launch_rollout_open(const CompArgs& a, cudaStream_t st) {
   return -1;
 }
 
+// ---- receding-horizon driver: apply the first control of each new plan to the TRUE system and shift the plan ----------
+// thread = problem.  x+ = f(x, l_0) + w with w injected (n per problem and step), Philox N(0, W) or the true-model
+// Gaussian mixture; the plan l (m x N, host layout) becomes the next warm start: u_init[k] = l[k+1], last control repeated.
+template <class D>
+__global__ void k_mpc_advance(MpcArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.P) return;
+  constexpr int n = D::n, m = D::m;
+  const int N = a.N;
+  const double* l = a.plan + (size_t)p * m * N;
+  double x[n], u[m], xn[n], w[n];
+  for (int i = 0; i < n; ++i) x[i] = a.x[(size_t)p * n + i];
+  for (int j = 0; j < m; ++j) u[j] = l[j];
+  int st = D::f(a.mp, x, u, xn) ? 0 : RATILQR_ST_DOMAIN;
+  if (a.noise) { for (int i = 0; i < n; ++i) w[i] = a.noise[((size_t)p * a.steps + a.t) * n + i]; }
+  else if (a.mix.k > 0) philox_mixture_noise<n>(a.seed, (uint64_t)(a.p0 + p), (uint32_t)a.t, a.mix, w);
+  else philox_noise<n>(a.seed, (uint64_t)(a.p0 + p), (uint32_t)a.t, 0, 1.0, a.cholW, w);
+  for (int i = 0; i < n; ++i) {
+    const double v = st ? (double)NAN : xn[i] + w[i];
+    a.x[(size_t)p * n + i] = v;
+    a.x_traj[((size_t)p * (a.steps + 1) + a.t + 1) * n + i] = v;
+  }
+  for (int j = 0; j < m; ++j) a.u_traj[((size_t)p * a.steps + a.t) * m + j] = u[j];
+  double* ui = a.u_init + (size_t)p * m * N;
+  for (int k = 0; k < N; ++k)
+    for (int j = 0; j < m; ++j) ui[(size_t)k * m + j] = l[(size_t)(k + 1 < N ? k + 1 : N - 1) * m + j];
+  a.theta_traj[(size_t)p * a.steps + a.t] = a.theta_opt[p];
+  a.value_traj[(size_t)p * a.steps + a.t] = a.value[p];
+  if (st) atomicMax(a.err, st);
+}
+
+int launch_mpc_advance(const MpcArgs& a, cudaStream_t st) {
+#define X(MID, CID) if (a.model_id == MID) { k_mpc_advance<Dyn<MID>><<<RL_BLOCKS(a.P, 64), 64, 0, st>>>(a); return 0; }
+  RL_FOR_EACH_ILEQG_COMBO(X)
+#undef X
+  return -1;
+}
+
 int launch_rollout_closed(const CompArgs& a, cudaStream_t st) {
 #define X(MID, CID) if (a.model_id == MID && a.cost_id == CID) { k_rollout_closed<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>><<<RL_BLOCKS(a.B, 64), 64, 0, st>>>(a); return 0; }
   RL_FOR_EACH_ILEQG_COMBO(X)

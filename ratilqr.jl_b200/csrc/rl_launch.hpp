@@ -94,6 +94,22 @@ void launch_nm_candidates(const NmFleet& c, cudaStream_t st);
 void launch_nm_decide(const NmFleet& c, cudaStream_t st);
 void launch_nm_final(const NmFleet& c, double* theta_final, const double* value, const int32_t* status, int stage, cudaStream_t st);
 
+// ---- receding-horizon MPC driver (ratilqr_mpc_fleet_run): true-system step + plan shift, one thread per problem -----
+struct MpcArgs {
+  int model_id, N, P, steps, t;
+  long long p0;                 // global index of this block's first problem (Philox stream)
+  double mp[8];
+  const double* plan;           // m*N*P  l_array of the plans just computed (host layout, device memory)
+  double* x;                    // n*P    current true states (in/out)
+  double* u_init;               // m*N*P  warm start of the next step (out)
+  const double* noise;          // n*steps*P injected disturbances (per problem: n x steps), or null
+  const double* cholW; uint64_t seed; rl::MixtureView mix;
+  const double *theta_opt, *value;        // per-problem results of this step's plan
+  double *x_traj, *u_traj, *theta_traj, *value_traj;  // n*(steps+1)*P, m*steps*P, steps*P, steps*P (problem slowest)
+  int32_t* err;
+};
+int launch_mpc_advance(const MpcArgs& a, cudaStream_t st);
+
 // DFMA throughput probe: returns total flops issued
 double launch_fp64_probe(double* sink, int iters, cudaStream_t st);
 

@@ -55,3 +55,18 @@ def run_fleet_mpc(be, problem, cost_params, x0, steps, kl_bound=0.1, rng=None, n
         xs[:, t + 1] = xn[:, 1] + w
         plan = np.concatenate([l[:, 1:], l[:, -1:]], axis=1)  # shift, repeat the last control
     return dict(x=xs, u=us, theta=thetas, value=values, ms=ms, mu_init=mu_i, sigma_init=sg_i)
+
+
+def run_fleet_mpc_on_device(be, problem, cost_params, x0, steps, kl_bound=0.1, u_init=None, noise=None, noise_seed=0,
+                            true_mixture=None, num_samples=10, num_elite=3, iter_max=5, mu_init=1.0, sigma_init=2.0, seed=0,
+                            z_inject=None, opts=None):
+    """The same receding-horizon loop with EVERY step on the device (`ratilqr_mpc_fleet_run`): planning (CE loop + final
+    solve), the true-system step x+ = f(x, l_0) + w, the disturbance draw (Philox N(0, W), the true-model mixture, or an
+    injected tensor `noise` (n, steps, P)) and the plan shift; states, plans and noise never visit the host.
+    Returns dict(x (n, steps+1, P), u (m, steps, P), theta (steps, P), value (steps, P), ms (steps,), mu_init, sigma_init)."""
+    spec = problem.spec(cost_params=cost_params)
+    if u_init is None:
+        u_init = np.zeros((spec.m, spec.N))
+    return be.mpc_fleet_run(spec, x0, u_init, steps, kl_bound, mu_init, sigma_init, num_samples=num_samples, num_elite=num_elite,
+                            iter_max=iter_max, z_inject=z_inject, seed=seed, noise=noise, noise_seed=noise_seed,
+                            true_mixture=true_mixture, opts=opts)
