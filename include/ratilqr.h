@@ -381,6 +381,66 @@ int32_t ratilqr_user_model_check(const ratilqr_user_model_desc* um, char* log, i
 int32_t ratilqr_user_model_register(ratilqr_ctx* ctx, const ratilqr_user_model_desc* um,
                                     int32_t* model_id_out, char* log, int64_t log_cap);
 
+/* ---- multi-GPU ---------------------------------------------------------------------------------
+ * The reference's only parallelism is a scatter of independent samples + a gather of one cost per sample
+ * (remotecall_fetch, cross_entropy_bilevel_optimization.jl:180-193, pets.jl:108-125).  Here a context can own an NCCL
+ * communicator (loaded at run time); the *_sharded calls are collective: EVERY rank of the communicator calls them with
+ * the same arguments, solves / rolls out its contiguous block of the population, and one ncclAllGather on DEVICE buffers
+ * hands every rank the whole cost vector; elite selection then runs redundantly and deterministically on every rank, so
+ * the CE state stays replicated without a broadcast.  Fleets of independent problems need no collective at all.
+ *   multi-process (one process per GPU):  rank 0 calls ratilqr_nccl_unique_id, the 128 bytes travel to the other ranks
+ *                                         by any means, every rank calls ratilqr_attach_comm on its ctx;
+ *   single process, several GPUs:         ratilqr_create_multi (ncclCommInitAll) and the ratilqr_multi_* calls, which run
+ *                                         the sharded call of every device on its own host thread. */
+int32_t ratilqr_nccl_unique_id(uint8_t* id128);
+int32_t ratilqr_attach_comm(ratilqr_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world);
+int32_t ratilqr_comm_info(const ratilqr_ctx* ctx, int32_t* rank, int32_t* world);
+/* compute_cost for ONE problem's K-sample population (x0 n, u_init m*N, theta K): cost K, status K on every rank */
+int32_t ratilqr_ce_costs_sharded(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                                 const double* x0, const double* u_init, const double* theta, int32_t K,
+                                 double kl_bound, double* cost, int32_t* status);
+/* ratilqr_ce_solve with the theta population of every CE iteration sharded (num_samples >= world size) */
+int32_t ratilqr_ce_solve_sharded(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                                 const ratilqr_ce_opts* ce, const double* x0, const double* u_init, double kl_bound,
+                                 const double* z_inject, int64_t nz, uint64_t seed,
+                                 double* mu_init, double* sigma_init,
+                                 double* theta_opt, double* value, double* theta_min, double* theta_max,
+                                 double* mu, double* sigma, int64_t* nz_used, int32_t* rounds,
+                                 ratilqr_ileqg_out* final);
+/* ratilqr_pets_costs with the C action sequences sharded; Philox streams are indexed by the global sequence / particle
+ * number, so the costs do not depend on the world size */
+int32_t ratilqr_pets_costs_sharded(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc,
+                                   const ratilqr_generative_desc* gen, const double* x0,
+                                   const double* controls, int32_t C, int32_t particles,
+                                   const double* noise, uint64_t seed, double* cost);
+
+typedef struct ratilqr_multi ratilqr_multi;
+int32_t ratilqr_create_multi(ratilqr_multi** out, const int32_t* device_ids, int32_t n_dev);
+int32_t ratilqr_destroy_multi(ratilqr_multi* mg);
+int32_t ratilqr_multi_size(const ratilqr_multi* mg);
+ratilqr_ctx* ratilqr_multi_ctx(ratilqr_multi* mg, int32_t i);
+const char* ratilqr_multi_last_error(const ratilqr_multi* mg);
+int32_t ratilqr_multi_ce_costs(ratilqr_multi* mg, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                               const double* x0, const double* u_init, const double* theta, int32_t K,
+                               double kl_bound, double* cost, int32_t* status);
+int32_t ratilqr_multi_ce_solve(ratilqr_multi* mg, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                               const ratilqr_ce_opts* ce, const double* x0, const double* u_init, double kl_bound,
+                               const double* z_inject, int64_t nz, uint64_t seed,
+                               double* mu_init, double* sigma_init,
+                               double* theta_opt, double* value, double* theta_min, double* theta_max,
+                               double* mu, double* sigma, int64_t* nz_used, int32_t* rounds,
+                               ratilqr_ileqg_out* final);
+int32_t ratilqr_multi_pets_costs(ratilqr_multi* mg, const ratilqr_problem_desc* desc,
+                                 const ratilqr_generative_desc* gen, const double* x0,
+                                 const double* controls, int32_t C, int32_t particles,
+                                 const double* noise, uint64_t seed, double* cost);
+/* fleet of P independent RAT iLQR problems block-partitioned over the devices, no collective; l_out m*N*P or NULL */
+int32_t ratilqr_multi_ce_solve_fleet(ratilqr_multi* mg, const ratilqr_problem_desc* desc,
+                                     const ratilqr_ileqg_opts* opts, const ratilqr_ce_opts* ce, int32_t P,
+                                     const double* x0, const double* u_init, int32_t u_count, double kl_bound,
+                                     uint64_t seed, double* mu_init, double* sigma_init,
+                                     double* theta_opt, double* value, double* l_out);
+
 /* ---- measurement utilities --------------------------------------------------------- */
 /* dependent-chain-free DFMA loop on every SM: returns achieved TFLOP/s (FP64, non-tensor) */
 int32_t ratilqr_fp64_peak_probe(ratilqr_ctx* ctx, double* tflops, float* ms);

@@ -5,7 +5,7 @@ modules because Python has no multiple dispatch: `ileqg.solve_`, `cross_entropy.
 """
 from . import cross_entropy, ileqg, models, mpc, nelder_mead, pets  # noqa: F401
 from ._capi import ApiError, Spec, make_opts  # noqa: F401
-from ._lib import default_backend, load_library, new_backend, set_default_backend  # noqa: F401
+from ._lib import default_backend, load_library, new_backend, new_multi, set_default_backend  # noqa: F401
 from .cross_entropy import CrossEntropyBilevelOptimizationSolver, InjectedNormals  # noqa: F401
 from .ileqg import (ILEQGSolver, NotPositiveDefinite, approximate_model, decrease_mu_and_delta_,  # noqa: F401
                     increase_mu_and_delta_, integrate_cost, line_search_, simulate_dynamics,

@@ -194,11 +194,18 @@ class CApi:
                                                       dp, dp, ip, ip, OUT])
         self.f_mpc = self._fn("mpc_fleet_run", [vp, PD, IO, C.POINTER(CeOpts), C.POINTER(MpcOpts), i32, dp, dp, i32, f64, dp, C.c_int64,
                                                 C.c_uint64, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_float), C.POINTER(i32)])
+        u8p = C.POINTER(C.c_uint8)
+        self.f_uid = self._fn("nccl_unique_id", [u8p])
+        self.f_attach = self._fn("attach_comm", [vp, u8p, i32, i32])
+        self.f_ce_costs_sh = self._fn("ce_costs_sharded", [vp, PD, IO, dp, dp, dp, i32, f64, dp, ip])
+        self.f_pets_costs_sh = self._fn("pets_costs_sharded", [vp, PD, GD, dp, dp, i32, i32, dp, C.c_uint64, dp])
         # (the oracle exports oracle_ce_solve / oracle_nm_solve with its OWN, older argument lists -- the tests call those
         #  directly -- so the single-problem entry points are bound for the product library only)
         one = (lambda name, at: self._fn(name, at)) if self.needs_ctx else (lambda name, at: self._fn("__absent__" + name, at))
         self.f_ce_one = one("ce_solve", [vp, PD, IO, C.POINTER(CeOpts), dp, dp, f64, dp, C.c_int64, C.c_uint64, dp, dp, dp, dp,
                                               dp, dp, dp, dp, C.POINTER(C.c_int64), C.POINTER(i32), OUT])
+        self.f_ce_one_sh = one("ce_solve_sharded", [vp, PD, IO, C.POINTER(CeOpts), dp, dp, f64, dp, C.c_int64, C.c_uint64, dp, dp, dp,
+                                                    dp, dp, dp, dp, dp, C.POINTER(C.c_int64), C.POINTER(i32), OUT])
         self.f_nm_one = one("nm_solve", [vp, PD, IO, C.POINTER(NmOpts), dp, dp, f64, dp, dp, dp, dp, ip, dp, dp, ip, ip, OUT])
         self.f_stage = self._fn("ileqg_stage", [vp, PD, IO, BI])
         self.f_run = self._fn("ileqg_run", [vp, i32, C.POINTER(C.c_float)])
@@ -350,9 +357,48 @@ class CApi:
         res["mu_init"], res["sigma_init"], res["rounds"] = mu_i, sg_i, int(rounds.value)
         return res
 
+    # ---- multi-GPU: NCCL communicator owned by the ctx (include/ratilqr.h "multi-GPU") ------------------------------
+    def nccl_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        self._check(self.f_uid(buf), "nccl_unique_id")
+        return bytes(buf)
+
+    def attach_comm(self, uid, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._check(self.f_attach(self.ctx, buf, int(rank), int(world)), "attach_comm")
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
+    def ce_costs_sharded(self, spec, x0, u_init, theta, kl_bound, opts=None):
+        """collective: compute_cost of one problem's theta population, block-sharded over the ranks of the attached
+        communicator; the all-gather runs inside the library on device buffers.  Every rank gets (cost, status)."""
+        opts = opts or make_opts()
+        theta = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
+        x0f, uf = _f64(x0), _f64(u_init)
+        cost, status = np.empty(theta.size), np.empty(theta.size, np.int32)
+        d = spec.desc()
+        self._check(self.f_ce_costs_sh(self.ctx, C.byref(d), C.byref(opts), _dp(x0f), _dp(uf), _dp(theta), theta.size,
+                                       float(kl_bound), _dp(cost), _ip(status)), "ce_costs_sharded")
+        return cost, status
+
+    def pets_costs_sharded(self, spec, x0, controls, particles, noise=None, seed=0, gen=None):
+        """collective: PETS compute_cost with the action sequences block-sharded over the ranks"""
+        n, m, N = spec.n, spec.m, spec.N
+        cf = _f64(controls)
+        Cn = cf.size // (m * N)
+        nf = None if noise is None else _f64(noise)
+        cost = np.zeros(Cn)
+        g, keep = self._gen(gen)
+        x0f = _f64(x0)
+        d = spec.desc()
+        self._check(self.f_pets_costs_sh(self.ctx, C.byref(d), C.byref(g), _dp(x0f), _dp(cf), Cn, int(particles), _dp(nf), int(seed),
+                                         _dp(cost)), "pets_costs_sharded")
+        del keep
+        return cost
+
     def ce_solve(self, spec, x0, u_init, kl_bound, mu_init, sigma_init, num_samples=10, num_elite=3, iter_max=5, lam=0.5,
-                 use_theta_max=False, z_inject=None, seed=0, opts=None):
-        """solve!(::CrossEntropyBilevelOptimizationSolver) for ONE problem, whole loop on the device (ratilqr_ce_solve)."""
+                 use_theta_max=False, z_inject=None, seed=0, opts=None, sharded=False):
+        """solve!(::CrossEntropyBilevelOptimizationSolver) for ONE problem, whole loop on the device (ratilqr_ce_solve);
+        sharded: collective over the attached communicator (ratilqr_ce_solve_sharded)."""
         opts = opts or make_opts()
         n, m, N = spec.n, spec.m, spec.N
         x0f, uf = _f64(x0), _f64(u_init)
@@ -368,10 +414,11 @@ class CApi:
         ce = CeOpts(int(num_samples), int(num_elite), int(iter_max), float(lam), int(bool(use_theta_max)))
         rounds = C.c_int32(0)
         d = spec.desc()
-        self._check(self.f_ce_one(self.ctx, C.byref(d), C.byref(opts), C.byref(ce), _dp(x0f), _dp(uf), float(kl_bound), _dp(zf), nz,
+        fn = self.f_ce_one_sh if sharded else self.f_ce_one
+        self._check(fn(self.ctx, C.byref(d), C.byref(opts), C.byref(ce), _dp(x0f), _dp(uf), float(kl_bound), _dp(zf), nz,
                                   int(seed), _dp(mu_i), _dp(sg_i), _dp(sc["theta_opt"]), _dp(sc["value"]), _dp(sc["theta_min"]),
                                   _dp(sc["theta_max"]), _dp(sc["mu"]), _dp(sc["sigma"]), nzu.ctypes.data_as(C.POINTER(C.c_int64)),
-                                  C.byref(rounds), C.byref(out)), "ce_solve")
+       C.byref(rounds), C.byref(out)), "ce_solve")
         res = {k: float(v[0]) for k, v in sc.items()}
         res.update(mu_init=float(mu_i[0]), sigma_init=float(sg_i[0]), nz_used=int(nzu[0]), rounds=int(rounds.value),
                    status=int(st[0]), iters=int(it[0]), x=x, l=l, L=L)
@@ -700,3 +747,116 @@ class CApi:
                                       int(num_elite), int(iter_max), float(smoothing), _dp(zf), _dp(nf), int(seed),
                                       _dp(mu_o), _dp(Sg_o)), "pets_solve")
         return mu_o.reshape((m, N), order="F"), Sg_o.reshape((m, m, N), order="F")
+
+
+class Multi:
+    """One process driving several GPUs (ratilqr_create_multi: contexts + NCCL communicators from ncclCommInitAll).
+    ce_costs / ce_solve / pets_costs shard ONE population over the devices (all-gather of the cost vector inside the
+    library, device buffers); ce_solve_fleet block-partitions independent problems (no collective)."""
+
+    def __init__(self, cdll, device_ids):
+        self.dll = cdll
+        ids = (C.c_int32 * len(device_ids))(*[int(d) for d in device_ids])
+        self.h = C.c_void_p()
+        f = cdll.ratilqr_create_multi
+        f.restype = C.c_int32
+        f.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32]
+        rc = f(C.byref(self.h), ids, len(device_ids))
+        if rc:
+            raise ApiError(f"ratilqr_create_multi failed ({rc}): needs {len(device_ids)} CUDA devices and NCCL; there is no CPU fallback")
+        self.n_dev = len(device_ids)
+        cdll.ratilqr_multi_last_error.restype = C.c_char_p
+        cdll.ratilqr_multi_last_error.argtypes = [C.c_void_p]
+        PD, IO, OUT, GD = C.POINTER(ProblemDesc), C.POINTER(IleqgOpts), C.POINTER(IleqgOut), C.POINTER(GenerativeDesc)
+        dp, ip, i32, f64, vp = c_double_p, c_int32_p, C.c_int32, C.c_double, C.c_void_p
+
+        def fn(name, at):
+            g = getattr(cdll, "ratilqr_multi_" + name)
+            g.restype, g.argtypes = C.c_int32, at
+            return g
+        self.f_costs = fn("ce_costs", [vp, PD, IO, dp, dp, dp, i32, f64, dp, ip])
+        self.f_solve = fn("ce_solve", [vp, PD, IO, C.POINTER(CeOpts), dp, dp, f64, dp, C.c_int64, C.c_uint64, dp, dp, dp, dp, dp, dp,
+                                        dp, dp, C.POINTER(C.c_int64), C.POINTER(i32), OUT])
+        self.f_pets = fn("pets_costs", [vp, PD, GD, dp, dp, i32, i32, dp, C.c_uint64, dp])
+        self.f_fleet = fn("ce_solve_fleet", [vp, PD, IO, C.POINTER(CeOpts), i32, dp, dp, i32, f64, C.c_uint64, dp, dp, dp, dp, dp])
+
+    def close(self):
+        if self.h:
+            self.dll.ratilqr_destroy_multi.argtypes = [C.c_void_p]
+            self.dll.ratilqr_destroy_multi(self.h)
+            self.h = C.c_void_p()
+
+    def _check(self, rc, what):
+        if rc:
+            raise ApiError(f"ratilqr_multi_{what} failed ({rc}): {self.dll.ratilqr_multi_last_error(self.h).decode()}")
+
+    def ce_costs(self, spec, x0, u_init, theta, kl_bound, opts=None):
+        opts = opts or make_opts()
+        theta = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
+        x0f, uf = _f64(x0), _f64(u_init)
+        cost, status = np.empty(theta.size), np.empty(theta.size, np.int32)
+        d = spec.desc()
+        self._check(self.f_costs(self.h, C.byref(d), C.byref(opts), _dp(x0f), _dp(uf), _dp(theta), theta.size, float(kl_bound),
+                                 _dp(cost), _ip(status)), "ce_costs")
+        return cost, status
+
+    def ce_solve(self, spec, x0, u_init, kl_bound, mu_init, sigma_init, num_samples=10, num_elite=3, iter_max=5, lam=0.5,
+                 use_theta_max=False, z_inject=None, seed=0, opts=None):
+        opts = opts or make_opts()
+        n, m, N = spec.n, spec.m, spec.N
+        x0f, uf = _f64(x0), _f64(u_init)
+        zf, nz = None, 0
+        if z_inject is not None:
+            zf = np.ascontiguousarray(np.asarray(z_inject, dtype=np.float64).ravel())
+            nz = zf.size
+        sc = {k: np.zeros(1) for k in ("theta_opt", "value", "theta_min", "theta_max", "mu", "sigma")}
+        mu_i, sg_i = np.array([float(mu_init)]), np.array([float(sigma_init)])
+        nzu, st = np.zeros(1, np.int64), np.zeros(1, np.int32)
+        x, l, L = np.zeros((n, N + 1), order="F"), np.zeros((m, N), order="F"), np.zeros((m, n, N), order="F")
+        out = IleqgOut(_dp(x), _dp(l), _dp(L), None, _ip(st), None, None, None, None, None, None, 0)
+        ce = CeOpts(int(num_samples), int(num_elite), int(iter_max), float(lam), int(bool(use_theta_max)))
+        rounds = C.c_int32(0)
+        d = spec.desc()
+        self._check(self.f_solve(self.h, C.byref(d), C.byref(opts), C.byref(ce), _dp(x0f), _dp(uf), float(kl_bound), _dp(zf), nz,
+                                 int(seed), _dp(mu_i), _dp(sg_i), _dp(sc["theta_opt"]), _dp(sc["value"]), _dp(sc["theta_min"]),
+                                 _dp(sc["theta_max"]), _dp(sc["mu"]), _dp(sc["sigma"]), nzu.ctypes.data_as(C.POINTER(C.c_int64)),
+                                 C.byref(rounds), C.byref(out)), "ce_solve")
+        res = {k: float(v[0]) for k, v in sc.items()}
+        res.update(mu_init=float(mu_i[0]), sigma_init=float(sg_i[0]), nz_used=int(nzu[0]), rounds=int(rounds.value), x=x, l=l, L=L)
+        return res
+
+    def pets_costs(self, spec, x0, controls, particles, noise=None, seed=0, gen=None):
+        m, N = spec.m, spec.N
+        cf = _f64(controls)
+        Cn = cf.size // (m * N)
+        nf = None if noise is None else _f64(noise)
+        cost = np.zeros(Cn)
+        gen = gen or {}
+        ens = gen.get("ensemble_params")
+        ensf = None if ens is None else _f64(ens)
+        g = GenerativeDesc(int(gen.get("noise_kind", 0)), float(gen.get("noise_scale", 1.0)), int(gen.get("n_ensemble", 1)),
+                           _dp(ensf), None, 0)
+        x0f = _f64(x0)
+        d = spec.desc()
+        self._check(self.f_pets(self.h, C.byref(d), C.byref(g), _dp(x0f), _dp(cf), Cn, int(particles), _dp(nf), int(seed), _dp(cost)),
+                    "pets_costs")
+        return cost
+
+    def ce_solve_fleet(self, spec, x0, u_init, kl_bound, mu_init, sigma_init, num_samples=10, num_elite=3, iter_max=5, lam=0.5,
+                       use_theta_max=False, seed=0, opts=None):
+        opts = opts or make_opts()
+        n, m, N = spec.n, spec.m, spec.N
+        x0 = np.asarray(x0, dtype=np.float64).reshape(n, -1)
+        P = x0.shape[1]
+        u_init = np.asarray(u_init, dtype=np.float64)
+        u_count = 1 if u_init.ndim == 2 else u_init.shape[-1]
+        x0f, uf = _f64(x0), _f64(u_init)
+        mu_i = np.ascontiguousarray(np.broadcast_to(np.asarray(mu_init, np.float64), (P,))).copy()
+        sg_i = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma_init, np.float64), (P,))).copy()
+        th, val = np.zeros(P), np.zeros(P)
+        l = np.zeros((m, N, P), order="F")
+        ce = CeOpts(int(num_samples), int(num_elite), int(iter_max), float(lam), int(bool(use_theta_max)))
+        d = spec.desc()
+        self._check(self.f_fleet(self.h, C.byref(d), C.byref(opts), C.byref(ce), P, _dp(x0f), _dp(uf), u_count, float(kl_bound),
+                                 int(seed), _dp(mu_i), _dp(sg_i), _dp(th), _dp(val), _dp(l)), "ce_solve_fleet")
+        return dict(theta_opt=th, value=val, l=l, mu_init=mu_i, sigma_init=sg_i)

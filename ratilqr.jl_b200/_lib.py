@@ -3,7 +3,7 @@ shared library is missing or no CUDA device can be opened, every solver call rai
 import ctypes
 import os
 
-from ._capi import CApi
+from ._capi import CApi, Multi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RATILQR_B200_LIB") or os.path.join(_HERE, "csrc", "libratilqr_b200.so")  # env override: tuning A/B runs
@@ -30,6 +30,11 @@ def load_library():
 def new_backend(device_id=0):
     """A fresh ctx on `device_id` (one ctx per device / per caller thread)."""
     return CApi(load_library(), "ratilqr_", needs_ctx=True).open(device_id)
+
+
+def new_multi(device_ids):
+    """One process, several GPUs: contexts + NCCL communicators (ratilqr_create_multi)."""
+    return Multi(load_library(), list(device_ids))
 
 
 def default_backend():

@@ -2,12 +2,14 @@
 // arrays into the device SoA workspace, kernel launches on the ctx stream, result download.
 // There is no CPU compute path in this file: every entry point ends in a kernel launch.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -70,6 +72,10 @@ struct ratilqr_ctx {
   DBuf s[16];
   DBuf d_mix[3];  // true-model noise mixture: cumulative weights, means, Cholesky factors
   DBuf d_cost;
+  // multi-GPU (ratilqr_attach_comm / ratilqr_create_multi): NCCL communicator of this ctx's device; rank / world of the group
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  DBuf d_sh[6];  // sharded population: theta, value, status (full size) and the padded all-gather buffers
   // receding-horizon driver (ratilqr_mpc_fleet_run): states / warm starts stay in d_x0 / d_u between the steps
   bool inputs_on_device = false;  // stage_internal: x0 / u_init are already in d_x0 / d_u (one block per problem)
   DBuf d_mpc[7];                  // x_traj, u_traj, theta_traj, value_traj, noise, cholW, err
@@ -86,6 +92,82 @@ struct ratilqr_ctx {
 
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
 
+static int check_launch(ratilqr_ctx* ctx, const char* what, int nlaunch = 1);
+// ---- NCCL, loaded at run time (dlopen, like NVRTC): the library still loads on boxes without NCCL, and inside a process
+// that already carries a libnccl.so.2 (torch) the loader hands back that copy instead of a second one ----------------------
+namespace nccl {
+typedef struct { char internal[128]; } UniqueId;  // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
+typedef int (*GetUniqueId_t)(UniqueId*);
+typedef int (*CommInitRank_t)(void**, int, UniqueId, int);
+typedef int (*CommInitAll_t)(void**, int, const int*);
+typedef int (*CommDestroy_t)(void*);
+typedef int (*AllGather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*GetErrorString_t)(int);
+static GetUniqueId_t GetUniqueId;
+static CommInitRank_t CommInitRank;
+static CommInitAll_t CommInitAll;
+static CommDestroy_t CommDestroy;
+static AllGather_t AllGather;
+static GetErrorString_t GetErrorString;
+constexpr int kInt32 = 2, kFloat64 = 8;  // ncclInt32, ncclFloat64
+static const char* load() {
+  static std::mutex mu;
+  static const char* err = nullptr;
+  static bool done = false;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done) return err;
+  done = true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return err = "libnccl.so.2 cannot be loaded (multi-GPU entry points need NCCL)";
+  GetUniqueId = (GetUniqueId_t)dlsym(h, "ncclGetUniqueId");
+  CommInitRank = (CommInitRank_t)dlsym(h, "ncclCommInitRank");
+  CommInitAll = (CommInitAll_t)dlsym(h, "ncclCommInitAll");
+  CommDestroy = (CommDestroy_t)dlsym(h, "ncclCommDestroy");
+  AllGather = (AllGather_t)dlsym(h, "ncclAllGather");
+  GetErrorString = (GetErrorString_t)dlsym(h, "ncclGetErrorString");
+  if (!GetUniqueId || !CommInitRank || !CommInitAll || !CommDestroy || !AllGather || !GetErrorString) return err = "libnccl.so.2 lacks an expected symbol";
+  return nullptr;
+}
+}  // namespace nccl
+#define NC(expr)                                                                                   \
+  do {                                                                                             \
+    int r__ = (expr);                                                                              \
+    if (r__ != 0) { ctx->err = std::string(#expr) + ": " + nccl::GetErrorString(r__); return -200 - r__; } \
+  } while (0)
+
+// sharded population: rank r owns the samples [S r / W, S (r+1) / W); blocks travel padded to ceil(S / W)
+__global__ void k_shard_pack(int cnt, const double* value, const int32_t* status, double* gv, int32_t* gs, int blk, int rank) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= blk) return;
+  gv[(size_t)rank * blk + i] = i < cnt ? value[i] : HUGE_VAL;
+  gs[(size_t)rank * blk + i] = i < cnt ? status[i] : -1;
+}
+__global__ void k_shard_unpack(int S, int W, int blk, const double* gv, const int32_t* gs, double* value, int32_t* status) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S) return;
+  int r = (int)(((long long)i * W + W - 1) / S);  // candidate owner; fix up below
+  while (r > 0 && (long long)S * r / W > i) --r;
+  while (r + 1 < W && (long long)S * (r + 1) / W <= i) ++r;
+  const int lo = (int)((long long)S * r / W);
+  value[i] = gv[(size_t)r * blk + (i - lo)];
+  if (status) status[i] = gs[(size_t)r * blk + (i - lo)];
+}
+// all-gather of the shard's (value, status) into full-size device arrays; every rank ends up with the same S entries
+static int shard_allgather(ratilqr_ctx* ctx, int S, int lo, int cnt, const double* value, const int32_t* status,
+                           double* value_full, int32_t* status_full) {
+  const int W = ctx->world, blk = (S + W - 1) / W;
+  (void)lo;
+  CU(ctx->d_sh[3].reserve((size_t)W * blk * 8)); CU(ctx->d_sh[4].reserve((size_t)W * blk * 4));
+  double* gv = ctx->d_sh[3].as<double>();
+  int32_t* gs = ctx->d_sh[4].as<int32_t>();
+  k_shard_pack<<<(blk + 127) / 128, 128, 0, ctx->stream>>>(cnt, value, status, gv, gs, blk, ctx->rank);
+  NC(nccl::AllGather(gv + (size_t)ctx->rank * blk, gv, (size_t)blk, nccl::kFloat64, ctx->comm, ctx->stream));  // in place
+  NC(nccl::AllGather(gs + (size_t)ctx->rank * blk, gs, (size_t)blk, nccl::kInt32, ctx->comm, ctx->stream));
+  k_shard_unpack<<<(S + 127) / 128, 128, 0, ctx->stream>>>(S, W, blk, gv, gs, value_full, status_full);
+  return check_launch(ctx, "k_shard_pack/unpack", 2);
+}
+
 static int upload(ratilqr_ctx* ctx, DBuf& b, const void* src, size_t bytes) {
   CU(b.reserve(bytes ? bytes : 8));
   if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -93,7 +175,7 @@ static int upload(ratilqr_ctx* ctx, DBuf& b, const void* src, size_t bytes) {
 }
 #define UP(buf, src, bytes) do { int rc__ = upload(ctx, buf, src, bytes); if (rc__) return rc__; } while (0)
 
-static int check_launch(ratilqr_ctx* ctx, const char* what, int nlaunch = 1) {
+static int check_launch(ratilqr_ctx* ctx, const char* what, int nlaunch) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); return -100 - (int)e; }
   ctx->launches += nlaunch;
@@ -527,6 +609,8 @@ int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
   for (DBuf& b : ctx->s) b.release();
   for (DBuf& b : ctx->d_mix) b.release();
   for (DBuf& b : ctx->d_mpc) b.release();
+  for (DBuf& b : ctx->d_sh) b.release();
+  if (ctx->comm && nccl::CommDestroy) nccl::CommDestroy(ctx->comm);
   ctx->d_order.release(); ctx->d_key.release();
   if (ctx->h_key) cudaFreeHost(ctx->h_key);
   for (rlu::Module* um : ctx->user_models) { rlu::unload(*um); delete um; }
@@ -1072,8 +1156,12 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
                                 int64_t nz, uint64_t seed, double* mu_init, double* sigma_init, double* theta_opt,
                                 double* value, double* theta_min, double* theta_max, double* mu, double* sigma,
                                 int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out,
-                                rll::MpcArgs* sink = nullptr) {
+                                rll::MpcArgs* sink = nullptr, bool sharded = false) {
   if (!ctx) return -1;
+  // sharded: ONE problem whose theta population is split over the ranks of ctx->comm (cross_entropy...jl:180-193 is the
+  // reference's fan-out): every rank draws the same population, solves its block, all-gathers (value, status) on device
+  // buffers and runs the elite selection redundantly, so the CE state stays replicated without a broadcast
+  if (sharded && (P != 1 || !ctx->comm || ctx->world < 2 || (ce && ce->num_samples < ctx->world))) FAIL(-1, "sharded CE needs one problem, an attached communicator and num_samples >= world size");
   if (!ce || P < 1 || !mu_init || !sigma_init || ((!theta_opt || !value) && !sink)) FAIL(-1, "bad arguments");
   if (!(kl_bound >= 0)) FAIL(-3, "KL Divergence Bound must be non-negative");  // :368
   if (ce->num_samples < 1 || ce->num_elite < 1 || ce->num_elite > ce->num_samples || ce->iter_max < 1) FAIL(-3, "bad CE options");
@@ -1095,8 +1183,12 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
   std::vector<double> init_tmin(P, HUGE_VAL), zeros(P, 0.0);
   std::vector<int32_t> ones(P, 1), izeros(P, 0);
   std::vector<long long> lzeros(P, 0);
+  const int sh_lo = sharded ? (int)((long long)S * ctx->rank / ctx->world) : 0;
+  const int sh_cnt = sharded ? (int)((long long)S * (ctx->rank + 1) / ctx->world) - sh_lo : S;
   if (kl_bound > 0) {
+    in.K = sh_cnt;
     if ((rc = stage_internal(ctx, desc, opts, &in, 0, true))) return rc;
+    in.K = S;
     UP(ctx->s[0], mu_init, Pb); UP(ctx->s[1], sigma_init, Pb);
     UP(ctx->s[2], mu_init, Pb); UP(ctx->s[3], sigma_init, Pb);          // initialize! :133-138: mu, sigma <- *_init
     UP(ctx->s[4], init_tmin.data(), Pb); UP(ctx->s[5], zeros.data(), Pb);  // theta_min = Inf, theta_max = 0
@@ -1123,6 +1215,11 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
   c.n_active = ctx->s[12].as<int32_t>();
   if (kl_bound > 0) {
     c.theta = ctx->d_theta.as<double>(); c.value = ctx->sp.value; c.status = ctx->sp.status;
+    if (sharded) {  // the population lives in full-size arrays; the solve kernel sees this rank's block of theta
+      CU(ctx->d_sh[0].reserve((size_t)S * 8)); CU(ctx->d_sh[1].reserve((size_t)S * 8)); CU(ctx->d_sh[2].reserve((size_t)S * 4));
+      c.theta = ctx->d_sh[0].as<double>(); c.value = ctx->d_sh[1].as<double>(); c.status = ctx->d_sh[2].as<int32_t>();
+      ctx->sp.theta = c.theta + sh_lo;
+    }
     ctx->sp.active = c.active;
     if (sort_fleet && !ctx->coop && P >= 64 && (int)ctx->fleet_key.size() == P) {  // previous call on a fleet of this size
       if ((rc = apply_slot_order(ctx, ctx->fleet_key, P, S))) return rc;
@@ -1131,6 +1228,7 @@ static int ce_solve_fleet_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* de
       rll::launch_ce_draw(c, st);
       if ((rc = check_launch(ctx, "k_ce_draw"))) return rc;
       if ((rc = run_internal(ctx, 1, nullptr))) return rc;
+      if (sharded && (rc = shard_allgather(ctx, S, sh_lo, sh_cnt, ctx->sp.value, ctx->sp.status, ctx->d_sh[1].as<double>(), ctx->d_sh[2].as<int32_t>()))) return rc;
       CU(cudaMemsetAsync(c.n_active, 0, 4, st));
       rll::launch_ce_update(c, ctx->s[14].as<double>(), st);
       if ((rc = check_launch(ctx, "k_ce_update"))) return rc;
@@ -1485,6 +1583,264 @@ int32_t ratilqr_nm_solve(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, con
                          double* theta_opt, double* value, int32_t* nm_iters, int32_t* n_evals, ratilqr_ileqg_out* final_out) {
   return ratilqr_nm_solve_fleet(ctx, desc, opts, nm, 1, x0, 1, u_init, 1, kl_bound, theta_high_init, theta_low_init, c_high,
                                 c_low, has_c, theta_opt, value, nm_iters, n_evals, final_out);
+}
+
+// ======== multi-GPU inside the C ABI: NCCL communicators owned by the contexts =========================
+int32_t ratilqr_nccl_unique_id(uint8_t* id128) {
+  if (!id128) return -1;
+  if (nccl::load()) return -20;
+  nccl::UniqueId id;
+  if (nccl::GetUniqueId(&id) != 0) return -21;
+  memcpy(id128, id.internal, 128);
+  return 0;
+}
+
+int32_t ratilqr_attach_comm(ratilqr_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world) {
+  if (!ctx) return -1;
+  if (!id128 || world < 1 || rank < 0 || rank >= world) FAIL(-1, "bad communicator description");
+  if (const char* e = nccl::load()) FAIL(-20, e);
+  if (ctx->comm) FAIL(-1, "a communicator is already attached to this ctx");
+  CU(cudaSetDevice(ctx->device));
+  nccl::UniqueId id;
+  memcpy(id.internal, id128, 128);
+  NC(nccl::CommInitRank(&ctx->comm, world, id, rank));
+  ctx->rank = rank; ctx->world = world;
+  return 0;
+}
+
+int32_t ratilqr_comm_info(const ratilqr_ctx* ctx, int32_t* rank, int32_t* world) {
+  if (!ctx) return -1;
+  if (rank) *rank = ctx->rank;
+  if (world) *world = ctx->comm ? ctx->world : 1;
+  return 0;
+}
+
+// compute_cost (cross_entropy...jl:173-195) of ONE problem's K-sample theta population, sharded: this rank solves its
+// block, one ncclAllGather of (value, status) on device buffers, cost = value + kl/theta for the whole population
+int32_t ratilqr_ce_costs_sharded(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                                 const double* x0, const double* u_init, const double* theta, int32_t K, double kl_bound,
+                                 double* cost, int32_t* status) {
+  if (!ctx) return -1;
+  if (!theta || !cost || K < 1) FAIL(-1, "bad arguments");
+  if (!ctx->comm || ctx->world < 2) FAIL(-1, "no communicator attached (ratilqr_attach_comm / ratilqr_create_multi)");
+  if (K < ctx->world) FAIL(-1, "population smaller than the world size");
+  const int W = ctx->world, lo = (int)((long long)K * ctx->rank / W), cnt = (int)((long long)K * (ctx->rank + 1) / W) - lo;
+  ratilqr_batch_in in;
+  in.P = 1; in.K = cnt; in.x0 = x0; in.x0_count = 1; in.u_init = u_init; in.u_count = 1; in.theta = theta + lo;
+  int rc = stage_internal(ctx, desc, opts, &in, 0);
+  if (rc) return rc;
+  if ((rc = run_internal(ctx, 1, nullptr))) return rc;
+  CU(ctx->d_sh[0].reserve((size_t)K * 8)); CU(ctx->d_sh[1].reserve((size_t)K * 8)); CU(ctx->d_sh[2].reserve((size_t)K * 4));
+  UP(ctx->d_sh[0], theta, (size_t)K * 8);
+  if ((rc = shard_allgather(ctx, K, lo, cnt, ctx->sp.value, ctx->sp.status, ctx->d_sh[1].as<double>(), ctx->d_sh[2].as<int32_t>()))) return rc;
+  CU(ctx->d_cost.reserve((size_t)K * 8));
+  k_ce_cost<<<(K + 127) / 128, 128, 0, ctx->stream>>>(K, ctx->d_sh[1].as<double>(), ctx->d_sh[2].as<int32_t>(), ctx->d_sh[0].as<double>(), kl_bound, ctx->d_cost.as<double>());
+  if ((rc = check_launch(ctx, "k_ce_cost"))) return rc;
+  CU(cudaMemcpyAsync(cost, ctx->d_cost.p, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CU(cudaMemcpyAsync(status, ctx->d_sh[2].p, (size_t)K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// solve!(::CrossEntropyBilevelOptimizationSolver) of ONE problem with the theta population sharded over the ranks
+int32_t ratilqr_ce_solve_sharded(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                                 const ratilqr_ce_opts* ce, const double* x0, const double* u_init, double kl_bound,
+                                 const double* z_inject, int64_t nz, uint64_t seed, double* mu_init, double* sigma_init,
+                                 double* theta_opt, double* value, double* theta_min, double* theta_max, double* mu,
+                                 double* sigma, int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out) {
+  if (!ctx) return -1;
+  return ce_solve_fleet_block(ctx, desc, opts, ce, 1, 0, x0, 1, u_init, 1, kl_bound, z_inject, nz, seed, mu_init, sigma_init,
+                              theta_opt, value, theta_min, theta_max, mu, sigma, nz_used, rounds_out, final_out, nullptr, true);
+}
+
+// compute_cost of PETS (pets.jl:100-126) sharded over the action sequences: this rank rolls out its block (Philox streams
+// are indexed by the GLOBAL sequence / particle number, so the result does not depend on the world size), one all-gather
+int32_t ratilqr_pets_costs_sharded(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const ratilqr_generative_desc* gen,
+                                   const double* x0, const double* controls, int32_t C, int32_t particles,
+                                   const double* noise, uint64_t seed, double* cost) {
+  if (!ctx) return -1;
+  if (!controls || !cost) FAIL(-1, "null argument");
+  if (!ctx->comm || ctx->world < 2) FAIL(-1, "no communicator attached (ratilqr_attach_comm / ratilqr_create_multi)");
+  if (C < ctx->world) FAIL(-1, "fewer action sequences than ranks");
+  const int W = ctx->world, lo = (int)((long long)C * ctx->rank / W), cnt = (int)((long long)C * (ctx->rank + 1) / W) - lo;
+  rll::PetsArgs a;
+  const rlu::Module* um = nullptr;
+  if (int rc = pets_fill(ctx, desc, gen, x0, cnt, particles, a, &um)) return rc;
+  const size_t n = desc->n, m = desc->m, N = desc->N;
+  UP(ctx->s[0], controls + m * N * lo, m * N * cnt * 8);
+  a.controls = ctx->s[0].as<double>();
+  if (noise) { UP(ctx->s[1], noise + n * N * (size_t)particles * lo, n * N * (size_t)particles * cnt * 8); a.noise = ctx->s[1].as<double>(); }
+  a.seed = seed; a.stream_offset = (uint64_t)lo * (uint64_t)particles;
+  CU(ctx->s[2].reserve((size_t)cnt * 8)); CU(ctx->d_sh[1].reserve((size_t)C * 8));
+  a.cost = ctx->s[2].as<double>();
+  if (int rc = pets_launch_costs(ctx, um, a)) return rc;
+  if (int rc = check_launch(ctx, "k_pets_costs", um ? 0 : 1)) return rc;
+  CU(ctx->d_sh[5].reserve((size_t)cnt * 4));
+  CU(cudaMemsetAsync(ctx->d_sh[5].p, 0, (size_t)cnt * 4, ctx->stream));
+  if (int rc = shard_allgather(ctx, C, lo, cnt, a.cost, ctx->d_sh[5].as<int32_t>(), ctx->d_sh[1].as<double>(), nullptr)) return rc;
+  DOWNSYNC(cost, ctx->d_sh[1].p, (size_t)C * 8);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- one process driving several GPUs: contexts + communicators from ncclCommInitAll, one host thread per device -----
+struct ratilqr_multi {
+  std::vector<ratilqr_ctx*> ctxs;
+  std::string err;
+};
+
+int32_t ratilqr_create_multi(ratilqr_multi** out, const int32_t* device_ids, int32_t n_dev) {
+  if (!out || !device_ids || n_dev < 1) return -1;
+  *out = nullptr;
+  if (n_dev > 1 && nccl::load()) return -20;
+  ratilqr_multi* mg = new ratilqr_multi();
+  for (int i = 0; i < n_dev; ++i) {
+    ratilqr_ctx* c = nullptr;
+    int rc = ratilqr_create(&c, device_ids[i]);
+    if (rc) { for (ratilqr_ctx* q : mg->ctxs) ratilqr_destroy(q); delete mg; return rc; }
+    mg->ctxs.push_back(c);
+  }
+  if (n_dev > 1) {
+    std::vector<void*> comms(n_dev, nullptr);
+    std::vector<int> devs(device_ids, device_ids + n_dev);
+    if (nccl::CommInitAll(comms.data(), n_dev, devs.data()) != 0) { for (ratilqr_ctx* q : mg->ctxs) ratilqr_destroy(q); delete mg; return -21; }
+    for (int i = 0; i < n_dev; ++i) { mg->ctxs[i]->comm = comms[i]; mg->ctxs[i]->rank = i; mg->ctxs[i]->world = n_dev; }
+  }
+  *out = mg;
+  return 0;
+}
+int32_t ratilqr_destroy_multi(ratilqr_multi* mg) {
+  if (!mg) return 0;
+  for (ratilqr_ctx* c : mg->ctxs) ratilqr_destroy(c);
+  delete mg;
+  return 0;
+}
+int32_t ratilqr_multi_size(const ratilqr_multi* mg) { return mg ? (int32_t)mg->ctxs.size() : 0; }
+ratilqr_ctx* ratilqr_multi_ctx(ratilqr_multi* mg, int32_t i) { return (mg && i >= 0 && i < (int)mg->ctxs.size()) ? mg->ctxs[i] : nullptr; }
+const char* ratilqr_multi_last_error(const ratilqr_multi* mg) { return mg ? mg->err.c_str() : "null handle"; }
+
+}  // extern "C"
+
+// runs fn(rank) on one host thread per device and returns the first failure; every rank's results land in rank 0's outputs
+template <class F>
+static int multi_run(ratilqr_multi* mg, F&& fn) {
+  const int W = (int)mg->ctxs.size();
+  std::vector<int> rcs(W, 0);
+  std::vector<std::thread> th;
+  for (int r = 1; r < W; ++r) th.emplace_back([&, r] { rcs[r] = fn(r); });
+  rcs[0] = fn(0);
+  for (auto& t : th) t.join();
+  for (int r = 0; r < W; ++r) if (rcs[r]) { mg->err = mg->ctxs[r]->err; return rcs[r]; }
+  return 0;
+}
+
+extern "C" {
+
+int32_t ratilqr_multi_ce_costs(ratilqr_multi* mg, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                               const double* x0, const double* u_init, const double* theta, int32_t K, double kl_bound,
+                               double* cost, int32_t* status) {
+  if (!mg || !cost || K < 1) return -1;
+  const int W = (int)mg->ctxs.size();
+  if (W == 1) {
+    ratilqr_batch_in in;
+    in.P = 1; in.K = K; in.x0 = x0; in.x0_count = 1; in.u_init = u_init; in.u_count = 1; in.theta = theta;
+    int rc = ratilqr_ce_costs(mg->ctxs[0], desc, opts, &in, kl_bound, cost, status);
+    if (rc) mg->err = mg->ctxs[0]->err;
+    return rc;
+  }
+  std::vector<std::vector<double>> c(W, std::vector<double>(K));
+  std::vector<std::vector<int32_t>> s(W, std::vector<int32_t>(K));
+  int rc = multi_run(mg, [&](int r) { return ratilqr_ce_costs_sharded(mg->ctxs[r], desc, opts, x0, u_init, theta, K, kl_bound, c[r].data(), s[r].data()); });
+  if (rc) return rc;
+  for (int r = 1; r < W; ++r)  // the gathered vectors are replicated: a cheap end-to-end check of the collective
+    if (memcmp(c[r].data(), c[0].data(), (size_t)K * 8) != 0) { mg->err = "ranks disagree on the gathered cost vector"; return -22; }
+  memcpy(cost, c[0].data(), (size_t)K * 8);
+  if (status) memcpy(status, s[0].data(), (size_t)K * 4);
+  return 0;
+}
+
+int32_t ratilqr_multi_ce_solve(ratilqr_multi* mg, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                               const ratilqr_ce_opts* ce, const double* x0, const double* u_init, double kl_bound,
+                               const double* z_inject, int64_t nz, uint64_t seed, double* mu_init, double* sigma_init,
+                               double* theta_opt, double* value, double* theta_min, double* theta_max, double* mu,
+                               double* sigma, int64_t* nz_used, int32_t* rounds_out, ratilqr_ileqg_out* final_out) {
+  if (!mg || !mu_init || !sigma_init || !theta_opt || !value) return -1;
+  const int W = (int)mg->ctxs.size();
+  if (W == 1) {
+    int rc = ratilqr_ce_solve(mg->ctxs[0], desc, opts, ce, x0, u_init, kl_bound, z_inject, nz, seed, mu_init, sigma_init, theta_opt,
+                              value, theta_min, theta_max, mu, sigma, nz_used, rounds_out, final_out);
+    if (rc) mg->err = mg->ctxs[0]->err;
+    return rc;
+  }
+  // every rank carries the whole (replicated) CE state; rank 0 writes the caller's outputs, the others scratch copies
+  struct Scratch { double mi, si, to, va, tmin, tmax, mu, sg; int64_t nzu; int32_t rounds; };
+  std::vector<Scratch> sc(W);
+  for (int r = 0; r < W; ++r) { sc[r].mi = *mu_init; sc[r].si = *sigma_init; }
+  int rc = multi_run(mg, [&](int r) {
+    Scratch& q = sc[r];
+    return ratilqr_ce_solve_sharded(mg->ctxs[r], desc, opts, ce, x0, u_init, kl_bound, z_inject, nz, seed, &q.mi, &q.si, &q.to, &q.va,
+                                    &q.tmin, &q.tmax, &q.mu, &q.sg, &q.nzu, &q.rounds, r == 0 ? final_out : nullptr);
+  });
+  if (rc) return rc;
+  for (int r = 1; r < W; ++r)
+    if (sc[r].to != sc[0].to || sc[r].mu != sc[0].mu || sc[r].nzu != sc[0].nzu) { mg->err = "ranks disagree on the replicated CE state"; return -22; }
+  *mu_init = sc[0].mi; *sigma_init = sc[0].si; *theta_opt = sc[0].to; *value = sc[0].va;
+  if (theta_min) *theta_min = sc[0].tmin;
+  if (theta_max) *theta_max = sc[0].tmax;
+  if (mu) *mu = sc[0].mu;
+  if (sigma) *sigma = sc[0].sg;
+  if (nz_used) *nz_used = sc[0].nzu;
+  if (rounds_out) *rounds_out = sc[0].rounds;
+  return 0;
+}
+
+int32_t ratilqr_multi_pets_costs(ratilqr_multi* mg, const ratilqr_problem_desc* desc, const ratilqr_generative_desc* gen,
+                                 const double* x0, const double* controls, int32_t C, int32_t particles, const double* noise,
+                                 uint64_t seed, double* cost) {
+  if (!mg || !cost || C < 1) return -1;
+  const int W = (int)mg->ctxs.size();
+  if (W == 1) {
+    int rc = ratilqr_pets_costs(mg->ctxs[0], desc, gen, x0, controls, C, particles, noise, seed, cost);
+    if (rc) mg->err = mg->ctxs[0]->err;
+    return rc;
+  }
+  std::vector<std::vector<double>> c(W, std::vector<double>(C));
+  int rc = multi_run(mg, [&](int r) { return ratilqr_pets_costs_sharded(mg->ctxs[r], desc, gen, x0, controls, C, particles, noise, seed, c[r].data()); });
+  if (rc) return rc;
+  memcpy(cost, c[0].data(), (size_t)C * 8);
+  return 0;
+}
+
+// fleet of independent RAT iLQR problems block-partitioned over the devices: no collective; results land
+// in the per-device slices of the caller's arrays; Philox streams are indexed by the global problem number
+int32_t ratilqr_multi_ce_solve_fleet(ratilqr_multi* mg, const ratilqr_problem_desc* desc, const ratilqr_ileqg_opts* opts,
+                                     const ratilqr_ce_opts* ce, int32_t P, const double* x0, const double* u_init,
+                                     int32_t u_count, double kl_bound, uint64_t seed, double* mu_init, double* sigma_init,
+                                     double* theta_opt, double* value, double* l_out) {
+  if (!mg || !desc || !ce || P < 1 || !x0 || !u_init || !mu_init || !sigma_init || !theta_opt || !value) return -1;
+  const int W = std::min((int)mg->ctxs.size(), (int)P);
+  if (desc->cost_params_count != 1 && desc->cost_params_count != P) { mg->err = "cost_params_count must be 1 or P"; return -1; }
+  const size_t n = desc->n, m = desc->m, N = desc->N;
+  std::vector<int> rcs(W, 0);
+  std::vector<std::thread> th;
+  auto run = [&](int r) {
+    const long long lo = (long long)P * r / W, hi = (long long)P * (r + 1) / W;
+    const int Pb = (int)(hi - lo);
+    ratilqr_problem_desc d = *desc;
+    if (desc->cost_params_count == P) { d.cost_params = desc->cost_params + (size_t)lo * desc->n_cost_params; d.cost_params_count = Pb; }
+    ratilqr_ileqg_out fo;
+    memset(&fo, 0, sizeof(fo));
+    if (l_out) fo.l = l_out + m * N * lo;
+    // Philox streams are indexed by the global problem number (p0 = lo): problem p draws what it would draw on one device
+    rcs[r] = ce_solve_fleet_block(mg->ctxs[r], &d, opts, ce, Pb, lo, x0 + n * lo, Pb, u_count == P ? u_init + m * N * lo : u_init,
+                                  u_count == P ? Pb : 1, kl_bound, nullptr, 0, seed, mu_init + lo, sigma_init + lo, theta_opt + lo,
+                                  value + lo, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, l_out ? &fo : nullptr);
+  };
+  for (int r = 1; r < W; ++r) th.emplace_back(run, r);
+  run(0);
+  for (auto& t : th) t.join();
+  for (int r = 0; r < W; ++r) if (rcs[r]) { mg->err = mg->ctxs[r]->err; return rcs[r]; }
+  return 0;
 }
 
 int32_t ratilqr_fp64_peak_probe(ratilqr_ctx* ctx, double* tflops, float* ms) {

@@ -25,9 +25,12 @@ static void launch_shape(const SolveParams& P, cudaStream_t st) {
   int blocks = (P.B + THREADS - 1) / THREADS;
   const size_t smem = UseStage<D>::value ? (size_t)2 * RL_STAGE_NV * THREADS * sizeof(double) : 0;
   static std::mutex cfg_mutex;  // sub-fleets launch from several host threads (ratilqr_ce_solve_fleet)
-  static bool configured = false;
+  static bool configured_dev[64] = {false};  // function attributes are per device (ratilqr_create_multi: several in one process)
   static int resident = MINB, sms = 148;
   std::lock_guard<std::mutex> cfg_lock(cfg_mutex);
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     configured = true;
     auto kfn = k_ileqg_solve<D, CT, THREADS, MINB>;
@@ -127,7 +130,10 @@ static int launch_coop_one(const SolveParams& P, double* traj_global, bool query
   if (smem_out) *smem_out = smem;
   if (query_only) return 0;
   auto kfn = k_ileqg_solve_coop<D, CT>;
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {0};  // per device (function attributes do not carry over to another GPU)
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  size_t& configured = configured_dev[cur_dev & 63];
   if (smem > configured) {
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);

@@ -18,6 +18,24 @@ def block_range(count, rank, world):
     return lo, hi
 
 
+def attach_library_comm(be, group=None):
+    """Gives the C library its own NCCL communicator over the ranks of `group` (one process per GPU): rank 0 creates the
+    NCCL unique id, torch.distributed only carries its 128 bytes to the other ranks, every rank calls ratilqr_attach_comm.
+    Afterwards the *_sharded calls all-gather on device buffers inside the library -- no host bounce, no torch tensors."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1 or getattr(be, "comm_world", 1) == world:
+        return be
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid = torch.tensor(list(be.nccl_unique_id()), dtype=torch.uint8, device=dev)
+    dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    be.attach_comm(bytes(uid.cpu().tolist()), rank, world)
+    return be
+
+
 def sharded_ce_costs(be, spec, x0, u_init, theta, kl_bound, opts=None, group=None):
     """compute_cost over a theta population split across the ranks of `group`; every rank returns the full
     cost vector.  Works with the nccl backend (GPU tensors) and gloo (CPU tensors, used by the tests)."""
@@ -27,6 +45,9 @@ def sharded_ce_costs(be, spec, x0, u_init, theta, kl_bound, opts=None, group=Non
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return be.ce_costs(spec, x0, u_init, theta, kl_bound, opts=opts)[0]
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if dist.get_backend(group) == "nccl" and theta.size >= world and hasattr(be, "ce_costs_sharded"):
+        attach_library_comm(be, group)  # GPU ranks: the all-gather runs inside the library on device buffers
+        return be.ce_costs_sharded(spec, x0, u_init, theta, kl_bound, opts=opts)[0]
     lo, hi = block_range(theta.size, rank, world)
     local = be.ce_costs(spec, x0, u_init, theta[lo:hi], kl_bound, opts=opts)[0] if hi > lo else np.zeros(0)
     return _all_gather_blocks(local, theta.size, group)  # num_samples doubles: latency-bound on NVLink 5 / NVSwitch

@@ -33,7 +33,7 @@ ok = bool(np.array_equal(full, single))
 flags = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(json.dumps({"check": "sharded_ce_costs over NCCL", "world": world, "thetas": 1024, "identical_on_all_ranks": bool(flags.item() == 1.0),
+    print(json.dumps({"check": "sharded_ce_costs: all-gather inside the C library (ratilqr_attach_comm + ratilqr_ce_costs_sharded), one process per GPU", "world": world, "thetas": 1024, "identical_on_all_ranks": bool(flags.item() == 1.0),
                       "ms_sharded": dt * 1e3, "elite_theta": float(theta[np.argsort(full, kind="stable")[0]])}))
 
 # ---- PETS (configs[3]): action sequences sharded, injected noise => bit-identical costs + redundant refit

@@ -99,3 +99,12 @@ def test_scalar_leqg_closed_form(oracle_be):
     Lc = -(b * St * a) / (r + b * St * b)
     S0 = q + a * St * a - (a * St * b) ** 2 / (r + b * St * b)
     assert np.isclose(out["L"][0, 0, 0, 0], Lc, rtol=1e-10) and np.isclose(out["S"][0, 0, 0, 0], S0, rtol=1e-10)
+
+
+def test_multi_gpu_handle_fails_loudly_without_devices():
+    """ratilqr_create_multi needs CUDA devices (and NCCL for more than one): no silent CPU path"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by scripts/check_multi_gpu.py")
+    with pytest.raises(R.ApiError, match="ratilqr_create_multi failed"):
+        R.new_multi([0, 1])
