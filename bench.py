@@ -15,7 +15,12 @@ value  : solves/s, kernel only, inputs resident in HBM, CUDA events on the libra
 e2e    : solves/s through the reference-facing call ratilqr_ce_costs (= compute_cost,
          cross_entropy_bilevel_optimization.jl:173-195) with HOST buffers: H2D of x0/u/theta/cost parameters and
          D2H of the cost + status vectors inside the timed region, every step.
-extra  : the exact configs[1] shape (1 problem x 1024 theta, latency-bound) is reported under "c2_single".
+extra  : "latency" = the small-batch cases of BASELINE.json with the CPU oracle timed beside each: configs[1] exactly
+         (1 problem x 1024 theta), a single problem's RAT iLQR MPC step (10 theta x 5 CE iterations + final solve, whole
+         loop on the device) and configs[2]'s RAT iLQR++ on the quadrotor; "roofline_c3" / "roofline_c4" = the
+         warp-cooperative (n = 12) solve kernel and the PETS rollout kernel against the FP64 roof.
+The CPU baseline / reference arm is the in-repo C++ ORACLE (a restatement of the Julia reference: there is no Julia in
+the image), all host threads, on a sample of problems drawn evenly from the SAME fleet; the sample is named in the line.
 """
 import argparse
 import json
@@ -108,20 +113,121 @@ def build_inputs(P, rank):
     return prob.spec(cost_params=cps), x0, u, theta
 
 
-def cpu_arm(spec_fn, sample_problems, steps, warmup):
-    """the oracle (CPU restatement of the reference) on all host threads, bounded sample of the same workload"""
+_FLEET_CACHE = {}
+
+
+def fleet_sample(P, count, shift=0):
+    """`count` problems taken evenly from rank 0's fleet of P problems (same generator, same theta populations): a sample
+    of the SAME workload, heavy (iter_max) and light problems in the fleet's own proportions.  `shift` rotates the
+    selection so that successive steps of the CPU arm measure DIFFERENT problems."""
+    from ratilqr_b200 import workloads as wl
+    if P not in _FLEET_CACHE:
+        _FLEET_CACHE[P] = wl.fleet(P, key=7)
+    prob, cps, x0, u = _FLEET_CACHE[P]
+    stride = max(P // max(count, 1), 1)
+    idx = np.unique((np.arange(count) * stride + shift * max(stride // 7, 1) + shift) % P)
+    theta = np.concatenate([wl.positive_thetas(THETAS, key=20201028 + int(p)) for p in idx])
+    return prob.spec(cost_params=cps[idx]), np.ascontiguousarray(x0[:, idx]), u, theta, idx
+
+
+def cpu_arm(P, steps, warmup, per_step):
+    """The oracle (CPU restatement of the reference) on all host threads.  Every step solves `per_step` problems x 1024
+    theta taken evenly from the same fleet, a different selection each step, so K steps sample K * per_step distinct
+    problems of the workload (about 5 % of the problems run to iter_max and cost 5x the median: a small fixed sample
+    would be a noisy estimate of the fleet's rate).  value = all solves / all time."""
     import oracle
     o = oracle.load()
     cores = int(o.raw.oracle_get_threads())
-    spec, x0, u, theta = spec_fn(sample_problems)
-    n_solves = theta.size
-    for _ in range(max(warmup, 0)):
-        o.ce_costs(spec, x0, u, theta, 0.1, P=sample_problems)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        o.ce_costs(spec, x0, u, theta, 0.1, P=sample_problems)
-    dt = (time.perf_counter() - t0) / steps
-    return n_solves / dt, cores, dt
+    for i in range(max(warmup, 0)):
+        spec, x0, u, theta, idx = fleet_sample(P, min(per_step, 4), shift=1000 + i)
+        o.ce_costs(spec, x0, u, theta, 0.1, P=len(idx))
+    times, solves, seen = [], 0, set()
+    for i in range(steps):
+        spec, x0, u, theta, idx = fleet_sample(P, per_step, shift=i)
+        t0 = time.perf_counter()
+        o.ce_costs(spec, x0, u, theta, 0.1, P=len(idx))
+        times.append(time.perf_counter() - t0)
+        solves += theta.size
+        seen.update(int(j) for j in idx)
+    total = float(np.sum(times))
+    sample = (f"{steps} step(s) x {per_step} problems x {THETAS} theta taken evenly from the {P}-problem fleet "
+              f"({len(seen)} distinct problems, {solves} solves, {total:.1f} s on {cores} threads; per-step rate "
+              f"{min(per_step * THETAS / t for t in times):.0f}-{max(per_step * THETAS / t for t in times):.0f} solves/s)")
+    return solves / total, cores, total / steps, sample, len(seen)
+
+
+def latency_cases(be, peak_tf, no_cpu):
+    """The small-batch cases of BASELINE.json (wall clock around blocking C-ABI calls, host buffers in and out), the CPU
+    oracle on all host threads beside each, and roofline-shaped figures for the n = 12 solve kernel and the PETS kernel."""
+    import oracle
+    import ratilqr_b200 as R
+    from ratilqr_b200 import cross_entropy as CE
+    from ratilqr_b200 import nelder_mead as NM
+    from ratilqr_b200 import workloads as wl
+    o = None if no_cpu else oracle.load()
+
+    def timed(fn, reps=5):
+        fn()
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); t.append(time.perf_counter() - t0)
+        return min(t) * 1e3
+
+    lat = {}
+    prob, x0, u = wl.c2_problem()
+    spec = prob.spec()
+    ua = [u[:, k].copy() for k in range(u.shape[1])]
+    th = wl.c2_thetas(THETAS)
+    g = timed(lambda: be.ce_costs(spec, x0, u, th, 0.1))
+    lat["c2_single_1x1024"] = {"what": "configs[1] exactly through ratilqr_ce_costs (compute_cost), host buffers", "gpu_ms": g,
+                               "gpu_solves_per_sec": THETAS / g * 1e3,
+                               "cpu_oracle_ms": None if no_cpu else timed(lambda: o.ce_costs(spec, x0, u, th, 0.1), 2)}
+    g = timed(lambda: be.ce_solve(spec, x0, u, 0.1, 1.0, 2.0, seed=3))
+
+    def cpu_mpc():
+        s = R.CrossEntropyBilevelOptimizationSolver(backend=o)
+        return CE.solve_(s, prob, x0, ua, np.random.default_rng(1), kl_bound=0.1)
+
+    lat["mpc_step_single_problem"] = {"what": "one RAT iLQR solve! (10 theta x 5 CE iterations + final solve), ratilqr_ce_solve: whole loop on the device",
+                                      "gpu_ms": g, "cpu_oracle_ms": None if no_cpu else timed(cpu_mpc, 3)}
+    p3, x03, u3 = wl.c3_problem()
+    ua3 = [u3[:, k].copy() for k in range(u3.shape[1])]
+
+    def nm(backend):
+        s = R.NelderMeadBilevelOptimizationSolver(backend=backend)
+        return NM.solve_(s, p3, x03, ua3, kl_bound=0.1)
+
+    lat["c3_rat_ilqr_pp_quadrotor"] = {"what": "configs[2]: RAT iLQR++ (Nelder-Mead defaults) on the 12-state quadrotor, T = 40, single problem",
+                                       "gpu_ms": timed(lambda: nm(be), 2), "cpu_oracle_ms": None if no_cpu else timed(lambda: nm(o), 2)}
+    if not no_cpu:
+        lat["cpu_threads"] = int(o.raw.oracle_get_threads())
+    # n = 12 solve kernel: 888 quadrotor iLEQG solves (6 per SM), algorithmic flops from the device counters
+    s3 = p3.spec()
+    B3 = 888
+    th3 = np.concatenate([[0.0], wl.positive_thetas(B3 - 1, mu=0.012, sigma=0.006, key=B3)])
+    be.stage(s3, x03, u3, th3)
+    be.run(1)
+    ms3 = be.run(3) / 3
+    r3 = be.fetch()
+    N3, F_LIN_Q, F_F_Q = 40, 400.0, 120.0  # quadrotor: Jacobians + quadratic cost derivatives, one dynamics step
+    it, tr = r3["iters"].astype(np.float64), r3["trials"].astype(np.float64)
+    fl3 = float(np.sum(N3 * (it * f_opt(12, 4) + (1 + tr) * f_eval(12, 4)) + (1 + it + tr) * N3 * F_LIN_Q + (1 + tr) * N3 * F_F_Q))
+    roof_c3 = {"bound": "fp64", "kernel": "k_ileqg_solve_coop<quadrotor, quadratic> (one warp per instance)", "achieved": fl3 / (ms3 * 1e-3) / 1e12,
+               "peak": peak_tf, "unit": "TFLOP/s", "frac": fl3 / (ms3 * 1e-3) / 1e12 / peak_tf, "instances": B3, "feasible": int((r3["status"] == 0).sum()),
+               "ms_per_launch": ms3, "solves_per_sec": B3 / ms3 * 1e3, "flops_per_launch": fl3,
+               "flops_per_stage": {"F_opt(12,4)": f_opt(12, 4), "F_eval(12,4)": f_eval(12, 4), "F_lin": F_LIN_Q, "F_f": F_F_Q}, "traffic": None}
+    # PETS: configs[3] in full, 5 CEM iterations; per particle N (F_f + F_c) + F_h flops (cart-pole step 45, quadratic cost 20)
+    p4, x04 = wl.c4_problem()
+    s4, gen = p4.spec(), p4.f_stochastic.gen()
+    mu0, Sg0 = np.zeros((1, 30)), np.tile(np.array([[4.0]])[:, :, None], (1, 1, 30))
+    ms4 = timed(lambda: be.pets_solve(s4, x04, mu0, Sg0, 4096, 150, 409, 5, 0.1, seed=1, gen=gen), 3)
+    fl4 = 4096.0 * 150 * 5 * (30 * (45.0 + 20.0) + 10.0)
+    roof_c4 = {"bound": "fp64", "kernel": "k_pets_costs<cartpole, quadratic> (+ Philox / Box-Muller noise, not counted)", "achieved": fl4 / (ms4 * 1e-3) / 1e12,
+               "peak": peak_tf, "unit": "TFLOP/s", "frac": fl4 / (ms4 * 1e-3) / 1e12 / peak_tf, "ms_per_solve": ms4,
+               "rollouts_per_sec": 4096 * 150 * 5 / ms4 * 1e3, "flops_per_solve": fl4,
+               "note": "end to end through ratilqr_pets_solve (sample, rollout, rank, refit x 5): the rollout kernel is SFU/latency bound "
+                       "(sincos of the dynamics, log/sqrt/sincos of Box-Muller), not FMA bound", "traffic": None}
+    return lat, roof_c3, roof_c4
 
 
 def main():
@@ -133,7 +239,8 @@ def main():
     ap.add_argument("--problems", type=int, default=1776, help="independent unicycle problems per GPU (x 1024 theta each)")
     ap.add_argument("--no-profile-warm", action="store_true", help="stage the timed launch without a previous call's work profile")
     ap.add_argument("--fleet-problems", type=int, default=8192, help="RAT iLQR problems per GPU for the MPC-step figure")
-    ap.add_argument("--cpu-sample-problems", type=int, default=2)
+    ap.add_argument("--cpu-sample-problems", type=int, default=0, help="problems per CPU step; 0 = 8 per step for the reference arm (a different selection every step), 48 for the in-run baseline")
+    ap.add_argument("--no-latency-cases", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -152,8 +259,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        value, cores, dt = cpu_arm(lambda P: build_inputs(P, 0), args.cpu_sample_problems, max(args.steps, 1), min(args.warmup, 1))
-        sample = f"{args.cpu_sample_problems} problems x {THETAS} theta = {args.cpu_sample_problems * THETAS} solves per step of the same workload"
+        value, cores, dt, sample, ns = cpu_arm(args.problems, max(args.steps, 1), min(args.warmup, 1), args.cpu_sample_problems or 8)
+        config["reference_arm_distinct_sample_problems"] = ns
+        config["reference_arm"] = "in-repo C++ oracle (restatement of the Julia reference; no Julia toolchain in the image)"
         print(json.dumps({"impl": "reference", "metric": "batched_ileqg_solves_per_sec", "value": value, "unit": "solves/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -214,13 +322,24 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = be.launch_count() - launches0
     clocks = sampler.stop()
+    ms_dev_rank = ms_dev
     ms_dev = max_over_ranks(ms_dev)
     ms_per_step = ms_dev / args.steps
     value = sum_over_ranks(float(B)) / (ms_per_step * 1e-3)
     res = be.fetch()
     ok = int(np.sum(res["status"] == 0))
-    flops = float(np.sum(algorithmic_flops(res["iters"], res["trials"])))
-    byts = float(np.sum(algorithmic_bytes(res["iters"], res["trials"])))
+    flops_rank = float(np.sum(algorithmic_flops(res["iters"], res["trials"])))
+    byts_rank = float(np.sum(algorithmic_bytes(res["iters"], res["trials"])))
+    # whole-job roofline: work summed over the ranks / the slowest rank's time (each rank draws its own fleet, so the
+    # ranks' work differs by a few percent: reported per rank below)
+    flops, byts = sum_over_ranks(flops_rank), sum_over_ranks(byts_rank)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([ms_dev_rank / args.steps, float(res["iters"].mean()), flops_rank, float(ok)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": r, "ms_per_step": float(t[0]), "mean_iters": float(t[1]), "algorithmic_flops": float(t[2]),
+                     "converged": int(t[3])} for r, t in enumerate(allr)]
 
     # ---- end to end through the reference-facing C-ABI call with host buffers --------------------------
     # Every call evaluates a FRESH theta population for the same fleet -- what consecutive CE iterations do
@@ -287,11 +406,16 @@ def main():
         except OSError:
             pass
         ach_gbs = byts / (ms_per_step * 1e-3) / 1e9
-        # the exact configs[1] shape: ONE problem x 1024 theta (latency-bound: 32 warps on a 148-SM device)
+        # the exact configs[1] shape: ONE problem x 1024 theta (latency-bound: the speculative kernel, rl_spec.cuh)
         s1, x01, u1, th1 = build_inputs(1, 0)
         be.stage(s1, x01, u1, th1, P=1)
         be.run(3)
         ms1 = be.run(args.steps) / args.steps
+        nominal_tf = 148 * 64 * 2 * 1.965e9 / 1e12              # SMs x FP64 lanes x 2 flops x boost clock (B200 datasheet-level)
+        clock_tf = 148 * 64 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12   # the same at the SM clock measured under load
+        latency, roof_c3, roof_c4 = None, None, None
+        if not args.no_latency_cases:
+            latency, roof_c3, roof_c4 = latency_cases(be, peak_tf, args.no_cpu_baseline)
         out = {"metric": "batched_ileqg_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world,
                "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -304,7 +428,10 @@ def main():
                             "traffic": traffic, "algorithmic_bytes_per_launch": byts, "kernel": "k_ileqg_solve<unicycle, quadratic>",
                             "peak_source": "burst DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 figure)",
                             "peak_sustained": peak_sus, "frac_of_sustained": ach_tf / peak_sus,
-                            "flops_per_launch": flops},
+                            "peak_nominal": nominal_tf, "frac_of_nominal": ach_tf / nominal_tf,
+                            "peak_at_measured_clock": clock_tf, "frac_of_peak_at_measured_clock": ach_tf / clock_tf,
+                            "flops_per_launch": flops,
+                            "flops_basis": "work summed over all ranks / slowest rank's time" if world > 1 else "this GPU"},
                "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
                "c2_single": {"workload": "configs[1] exactly: 1 problem x 1024 theta", "ms_per_batch": ms1,
@@ -317,10 +444,14 @@ def main():
                             "mc_eval": {"samples_per_problem": MC, "ms": mc_s * 1e3, "rollouts_per_sec": MC * Pf * world / mc_s,
                                         "problems_with_finite_mean": int(mc_finite),
                                         "call": "ratilqr_mc_rollout, host policy buffers in, J + stats out, Philox noise"}}}
+        if per_rank is not None:
+            out["per_rank"] = per_rank
+        if latency is not None:
+            out["latency"], out["roofline_c3"], out["roofline_c4"] = latency, roof_c3, roof_c4
         if not args.no_cpu_baseline:
-            v, cores, dt = cpu_arm(lambda PP: build_inputs(PP, 0), args.cpu_sample_problems, 1, 0)
-            out["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
-                                   "sample": f"{args.cpu_sample_problems} problems x {THETAS} theta of the same workload, {dt:.2f} s wall"}
+            v, cores, dt, sample, _ = cpu_arm(P, 1, 0, args.cpu_sample_problems or 48)
+            out["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample,
+                                   "what": "in-repo C++ oracle (restatement of the Julia reference), not Julia itself"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
