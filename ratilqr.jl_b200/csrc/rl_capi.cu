@@ -48,6 +48,7 @@ struct ratilqr_ctx {
   bool staged = false;
   int model_id = 0, cost_id = 0, n = 0, m = 0, N = 0, B = 0, eps_cap = 0;
   bool coop = false;          // staged solve runs on the warp-cooperative kernel
+  bool coop2 = false;         // ... on its two-warp speculative variant (small batches: latency)
   bool dynamic = false;       // staged solve uses the persistent kernel with lane-level refill
   int spec_G = 0;             // > 0: staged solve runs on the speculative latency kernel with this many lanes per instance
   bool traj_retained = false; // xo/lo/Lo hold the trajectories (coop / dynamic modes)
@@ -422,6 +423,16 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
       ctx->traj_retained = true;
     }
   }
+  ctx->coop2 = false;
+  if (ctx->coop) {
+    // small batches: the two-warp variant (pass speculation) while every instance still gets an SM share of its own
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const size_t c2 = rll::coop2_smem_query(desc->model_id, ctx->coop_cost_id, N);
+    const char* e = getenv("RATILQR_COOP2");  // 0 = never, 1 = whenever it fits (tuning / A-B runs)
+    const bool fits = c2 > 0 && c2 <= 200 * 1024;
+    ctx->coop2 = fits && (e ? e[0] == '1' : B <= (size_t)3 * sms);
+  }
   if (ctx->coop) {
     ctx->traj_retained = true;
     P.perm = nullptr;
@@ -443,6 +454,11 @@ static int run_internal(ratilqr_ctx* ctx, int reps, float* ms_total) {
   CU(cudaSetDevice(ctx->device));
   if (ms_total) CU(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int r = 0; r < reps; ++r) {
+    if (ctx->coop && ctx->coop2) {
+      if (rll::launch_solve_coop2(ctx->model_id, ctx->coop_cost_id, ctx->sp, ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
+      if (int rc = check_launch(ctx, "k_ileqg_solve_coop2")) return rc;
+      continue;
+    }
     if (ctx->coop) {
       if (rll::launch_solve_coop(ctx->model_id, ctx->coop_cost_id, ctx->sp, ctx->d_coop_traj.as<double>(), ctx->stream)) FAIL(-5, "this (model, cost) pair is not compiled in");
       if (int rc = check_launch(ctx, "k_ileqg_solve_coop")) return rc;

@@ -34,11 +34,48 @@ struct CoopWs {
   double T[n * n], U[n * m], g[m], G[m * n], H[m * m], CH[m * m], invh[m], L[m * n], dl[m], HL[m * n], Hdl[m];
   double x[n], u[m], xn[n], Sn[n * n], svn[n];
   double q, flag, nrm;  // stage cost value; domain-error flag; ||l - u||^2 of the rollout step
+  double sc[8];         // per-stage trigonometry shared by the lanes (CoopDyn<quadrotor>)
 };
 
 // per-instance trajectories, contiguous per instance: X[2][(N+1)*n], U[2][N*m], Lg[N*m*n], DL[N*m]
 struct CoopTraj {
   double *X, *U, *Lg, *DL;
+};
+
+// what one pass / rollout of an instance reads and writes (all contiguous per instance, stage-major):
+//   Xs, Us  trajectory swept by a backward pass / the nominal (xbar, l) a rollout starts from
+//   Xd, Ud  destination of a rollout
+//   Lr, DLr policy read: gains of an evaluating pass; gains and dl of a rollout
+//   Lw, DLw policy written by an optimising pass
+struct CoopIO {
+  const double *Xs, *Us;
+  double *Xd, *Ud;
+  const double *Lr, *DLr;
+  double *Lw, *DLw;
+};
+// the single-warp kernel's view: trajectory double buffer `buf` / `buf ^ 1`, one policy buffer
+RL_HD CoopIO coop_io(const CoopTraj& tj, int buf, int n, int m, int N) {
+  CoopIO io;
+  io.Xs = tj.X + (size_t)buf * (N + 1) * n; io.Us = tj.U + (size_t)buf * N * m;
+  io.Xd = tj.X + (size_t)(buf ^ 1) * (N + 1) * n; io.Ud = tj.U + (size_t)(buf ^ 1) * N * m;
+  io.Lr = tj.Lg; io.DLr = tj.DL; io.Lw = tj.Lg; io.DLw = tj.DL;
+  return io;
+}
+
+// Per-model hooks of the cooperative kernel.  trig(l, w): executed by lane l INSIDE the phase that precedes the model
+// evaluation (lanes 8.. are free there) -- values every lane of the next phase shares; f(): the dynamics step, run by
+// one lane.  Default: nothing to share.
+template <class D> struct CoopDyn {
+  template <int n, int m> RL_HD static void trig(int, CoopWs<n, m>&) {}
+  template <int n, int m> RL_HD static bool f(const double* mp, CoopWs<n, m>& w) { return D::f(mp, w.x, w.u, w.xn); }
+};
+// the quadrotor: sin / cos of the three Euler angles, one libm call per lane (lanes 8..13), instead of twelve calls in the
+// lane that steps the dynamics and twenty-four in each of the sixteen lanes that seed a dual-number direction
+template <> struct CoopDyn<Dyn<RATILQR_MODEL_QUADROTOR>> {
+  template <int n, int m> RL_HD static void trig(int l, CoopWs<n, m>& w) {
+    if (l >= 8 && l < 14) { const int a = 3 + ((l - 8) >> 1); w.sc[l - 8] = ((l - 8) & 1) ? cos(w.x[a]) : sin(w.x[a]); }
+  }
+  template <int n, int m> RL_HD static bool f(const double* mp, CoopWs<n, m>& w) { quadrotor_body_sc<double>(mp, w.x, w.u, w.xn, w.sc); return true; }
 };
 
 // models whose Jacobian comes from duals evaluate one seeded direction per lane
@@ -62,8 +99,15 @@ RL_HD void coop_dual_jac(int lane, Body body, const double* mp, CoopWs<n, m>& w)
 template <> struct CoopJac<Dyn<RATILQR_MODEL_CARTPOLE>> {
   template <int n, int m> RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w) { coop_dual_jac(lane, CartpoleBody(), mp, w); }
 };
+struct QuadrotorBodySc {  // the body with the shared trigonometry of CoopDyn<quadrotor>::trig
+  const double* sc;
+  template <class T> RL_HD void operator()(const double* p, const T* x, const T* u, T* xn) const { quadrotor_body_sc<T>(p, x, u, xn, sc); }
+};
 template <> struct CoopJac<Dyn<RATILQR_MODEL_QUADROTOR>> {
-  template <int n, int m> RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w) { coop_dual_jac(lane, QuadrotorBody(), mp, w); }
+  template <int n, int m> RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w) {
+    QuadrotorBodySc body; body.sc = w.sc;
+    coop_dual_jac(lane, body, mp, w);
+  }
 };
 
 // One Riccati stage, cooperative.  w.S / w.sv / s hold (S+, s_vec+, s+) on entry, the stage's values on exit.
@@ -270,14 +314,13 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
 
 // backward pass (approximate_model fused), cooperative; same contract as rl::backward_pass
 template <class D, class CT, bool OPT>
-RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, double theta, int buf, bool zeroL,
-                             double& mu, double& delta, int& restarts, double& value, CoopWs<D::n, D::m>& w,
-                             const CoopTraj& tj) {
+RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, double theta, const CoopIO& io, bool zeroL,
+                             double& mu, double& delta, int& restarts, double& value, CoopWs<D::n, D::m>& w) {
   constexpr int n = D::n, m = D::m;
   using Tr = StageTraits<D, CT>;
   const int N = P.N;
-  const double* Xb = tj.X + (size_t)buf * (N + 1) * n;
-  const double* Ub = tj.U + (size_t)buf * N * m;
+  const double* Xb = io.Xs;
+  const double* Ub = io.Us;
   while (true) {
     double s = 0.0;
     phase(lane, [&](int l) {
@@ -299,15 +342,17 @@ RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, d
     bool restart = false;
     double detprod = 1.0, logacc = 0.0;
     for (int k = N - 1; k >= 0; --k) {
-      double* Lk = tj.Lg + (size_t)k * m * n;
+      const double* Lrk = io.Lr + (size_t)k * m * n;
+      double* Lwk = io.Lw + (size_t)k * m * n;
       phase(lane, [&](int l) {
         for (int e = l; e < n + m + m * n; e += 32) {
           if (e < n) w.x[e] = Xb[(size_t)k * n + e];
           else if (e < n + m) w.u[e - n] = Ub[(size_t)k * m + (e - n)];
-          else if (!OPT) w.L[e - n - m] = zeroL ? 0.0 : Lk[e - n - m];
+          else if (!OPT) w.L[e - n - m] = zeroL ? 0.0 : Lrk[e - n - m];
         }
       });
       phase(lane, [&](int l) {
+        CoopDyn<D>::trig(l, w);
         if (l != 0) return;
         double q;
         w.flag = CT::stage(cp, k, w.x, w.u, true, q, w.qv, w.Q, w.r, w.R, w.Pm) ? 0.0 : 1.0;
@@ -330,7 +375,7 @@ RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, d
         }
         phase(lane, [&](int l) {
           for (int e = l; e < m * n + m; e += 32) {
-            if (e < m * n) Lk[e] = w.L[e]; else tj.DL[(size_t)k * m + (e - m * n)] = w.dl[e - m * n];
+            if (e < m * n) Lwk[e] = w.L[e]; else io.DLw[(size_t)k * m + (e - m * n)] = w.dl[e - m * n];
           }
         });
       }
@@ -345,31 +390,32 @@ RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, d
 
 // closed-loop / open-loop (init) rollout into buffer cur^1, cooperative
 template <class D>
-RL_HD int coop_rollout(int lane, const SolveParams& P, int cur, double eps, bool init, double& dmax,
-                       CoopWs<D::n, D::m>& w, const CoopTraj& tj) {
+RL_HD int coop_rollout(int lane, const SolveParams& P, const CoopIO& io, double eps, bool init, double& dmax,
+                       CoopWs<D::n, D::m>& w) {
   constexpr int n = D::n, m = D::m;
   const int N = P.N;
-  const double* Xc = tj.X + (size_t)cur * (N + 1) * n;
-  const double* Uc = tj.U + (size_t)cur * N * m;
-  double* Xn = tj.X + (size_t)(cur ^ 1) * (N + 1) * n;
-  double* Un = tj.U + (size_t)(cur ^ 1) * N * m;
+  const double* Xc = io.Xs;
+  const double* Uc = io.Us;
+  double* Xn = io.Xd;
+  double* Un = io.Ud;
   phase(lane, [&](int l) { for (int i = l; i < n; i += 32) { w.x[i] = Xc[i]; Xn[i] = Xc[i]; } });
   double best = -rl_inf();
   bool has_nan = false;
   for (int k = 0; k < N; ++k) {
-    const double* Lk = tj.Lg + (size_t)k * m * n;
+    const double* Lk = io.Lr + (size_t)k * m * n;
     phase(lane, [&](int l) {
+      CoopDyn<D>::trig(l, w);
       for (int j = l; j < m; j += 32) {
         const double lj = Uc[(size_t)k * m + j];
         double uj = lj;
         if (!init) {
           if (RL_FUSED) {
-            uj = lj + eps * tj.DL[(size_t)k * m + j];
+            uj = lj + eps * io.DLr[(size_t)k * m + j];
             for (int i = 0; i < n; ++i) uj = rl_fma(Lk[j + i * m], w.x[i] - Xc[(size_t)k * n + i], uj);
           } else {
             double a = Lk[j] * (w.x[0] - Xc[(size_t)k * n]);
             for (int i = 1; i < n; ++i) a = rl_fma(Lk[j + i * m], w.x[i] - Xc[(size_t)k * n + i], a);
-            uj = (lj + eps * tj.DL[(size_t)k * m + j]) + a;
+            uj = (lj + eps * io.DLr[(size_t)k * m + j]) + a;
           }
         }
         w.u[j] = uj;
@@ -382,7 +428,7 @@ RL_HD int coop_rollout(int lane, const SolveParams& P, int cur, double eps, bool
       double acc = w.g[0] * w.g[0];
       for (int j = 1; j < m; ++j) acc = rl_fma(w.g[j], w.g[j], acc);
       w.nrm = sqrt(acc);
-      w.flag = D::f(P.mp, w.x, w.u, w.xn) ? 0.0 : 1.0;
+      w.flag = CoopDyn<D>::f(P.mp, w) ? 0.0 : 1.0;
     });
     const double nr = w.nrm;
     if (nr != nr) has_nan = true;
@@ -421,7 +467,7 @@ RL_HD bool coop_solve_instance(int lane, const SolveParams& P, size_t inst, Coop
   while (true) {
     if (need_opt) {
       double dummy;
-      status = coop_backward_pass<D, CT, true>(lane, P, cp, theta, cur, false, mu, delta, restarts, dummy, w, tj);
+      status = coop_backward_pass<D, CT, true>(lane, P, cp, theta, coop_io(tj, cur, n, m, N), false, mu, delta, restarts, dummy, w);
       if (status) break;
       need_opt = false;
     }
@@ -430,9 +476,9 @@ RL_HD bool coop_solve_instance(int lane, const SolveParams& P, size_t inst, Coop
       if (eps == 0.0 || count > 4000) { status = RATILQR_ST_LINESEARCH_HANG; break; }
     }
     double dmax, nw;
-    status = coop_rollout<D>(lane, P, cur, eps, init, dmax, w, tj);
+    status = coop_rollout<D>(lane, P, coop_io(tj, cur, n, m, N), eps, init, dmax, w);
     if (status) break;
-    int rc = coop_backward_pass<D, CT, false>(lane, P, cp, theta, cur ^ 1, init, mu, delta, restarts, nw, w, tj);
+    int rc = coop_backward_pass<D, CT, false>(lane, P, cp, theta, coop_io(tj, cur ^ 1, n, m, N), init, mu, delta, restarts, nw, w);
     if (rc == RATILQR_ST_DOMAIN) { status = rc; break; }
     if (init) {
       if (rc) { status = RATILQR_ST_M_NOT_PD_INIT; break; }

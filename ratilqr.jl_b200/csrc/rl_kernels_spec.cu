@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "rl_coop2.cuh"
 #include "rl_spec.cuh"
 #include "rl_host.hpp"
 #include "rl_launch.hpp"
@@ -91,6 +92,75 @@ int launch_solve_spec(int model_id, int cost_id, int G, const SolveParams& P, cu
     return -1;                                                             \
   }
   RL_FOR_EACH_SPEC_COMBO(X)
+#undef X
+  return -1;
+}
+
+// ---- two-warp speculative variant of the warp-cooperative kernel (rl_coop2.cuh): one CTA of 64 threads per instance ----
+template <class D, class CT>
+__global__ void __launch_bounds__(64) k_ileqg_solve_coop2(const __grid_constant__ SolveParams P) {
+  extern __shared__ double coop2_smem[];
+  __shared__ SpecLaneRes res[2];
+  constexpr int n = D::n, m = D::m;
+  const int tid = threadIdx.x, g = tid >> 5, lane = tid & 31;
+  constexpr size_t wsd = (sizeof(CoopWs<n, m>) + 7) / 8;
+  CoopWs<n, m>& w = *reinterpret_cast<CoopWs<n, m>*>(coop2_smem + (size_t)g * wsd);
+  Coop2Traj t;
+  t.n = n; t.m = m; t.N = P.N;
+  t.X = coop2_smem + 2 * wsd; t.U = t.X + (size_t)3 * (P.N + 1) * n; t.Lg = t.U + (size_t)3 * P.N * m; t.DL = t.Lg + (size_t)2 * P.N * m * n;
+  const size_t inst = blockIdx.x;
+  const size_t p = inst / (size_t)P.K;
+  if (P.active && !P.active[p]) return;
+  const double* cp = P.cost_params + (P.cp_count > 1 ? p * (size_t)P.ncp : 0);
+  const double theta = P.theta[inst];
+  SpecState S;
+  spec_state_init(P, S);
+  while (!S.done) {
+    const SpecLaneRes r = coop2_warp_work<D, CT>(lane, g, P, S, cp, theta, p, w, t);
+    if (lane == 0) res[g] = r;
+    __syncthreads();
+    SpecLaneRes rr[2];
+    rr[0] = res[0]; rr[1] = res[1];
+    spec_decide<2>(P, S, rr, inst, tid == 0);
+    __syncthreads();
+  }
+  coop2_write_outputs(P, t, S, inst, tid, 64);
+}
+
+template <class D, class CT>
+static size_t coop2_smem_bytes(int N) {
+  return (2 * ((sizeof(CoopWs<D::n, D::m>) + 7) / 8) + coop2_traj_doubles(D::n, D::m, N)) * sizeof(double);
+}
+
+#define RL_FOR_EACH_COOP2_COMBO(X) X(RATILQR_MODEL_QUADROTOR, RATILQR_COST_QUADRATIC) X(RATILQR_MODEL_QUADROTOR, RL_COST_QUAD_DIAG)
+
+// bytes of dynamic shared memory one instance needs, or 0 if the pair is not served by this kernel
+size_t coop2_smem_query(int model_id, int cost_id, int N) {
+#define X(MID, CID) if (model_id == MID && cost_id == CID) return coop2_smem_bytes<Dyn<MID>, Cost<CID, Dyn<MID>::n, Dyn<MID>::m>>(N);
+  RL_FOR_EACH_COOP2_COMBO(X)
+#undef X
+  return 0;
+}
+
+int launch_solve_coop2(int model_id, int cost_id, const SolveParams& P, cudaStream_t st) {
+#define X(MID, CID)                                                                                      \
+  if (model_id == MID && cost_id == CID) {                                                               \
+    using D = Dyn<MID>;                                                                                  \
+    using CT = Cost<CID, D::n, D::m>;                                                                    \
+    const size_t smem = coop2_smem_bytes<D, CT>(P.N);                                                    \
+    auto kfn = k_ileqg_solve_coop2<D, CT>;                                                               \
+    static size_t configured_dev[64] = {0};                                                              \
+    int dev = 0;                                                                                         \
+    cudaGetDevice(&dev);                                                                                 \
+    if (smem > configured_dev[dev & 63]) {                                                               \
+      cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+      cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);                    \
+      configured_dev[dev & 63] = smem;                                                                   \
+    }                                                                                                    \
+    kfn<<<P.B, 64, smem, st>>>(P);                                                                       \
+    return 0;                                                                                            \
+  }
+  RL_FOR_EACH_COOP2_COMBO(X)
 #undef X
   return -1;
 }

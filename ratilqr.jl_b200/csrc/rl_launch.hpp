@@ -22,6 +22,10 @@ int launch_solve_coop(int model_id, int cost_id, const rl::SolveParams& P, doubl
 bool spec_supported(int model_id, int cost_id);
 int launch_solve_spec(int model_id, int cost_id, int G, const rl::SolveParams& P, cudaStream_t st);
 
+// two-warp speculative variant of the warp-cooperative kernel (rl_coop2.cuh): latency path of the n > 6 models
+size_t coop2_smem_query(int model_id, int cost_id, int N);
+int launch_solve_coop2(int model_id, int cost_id, const rl::SolveParams& P, cudaStream_t st);
+
 // SoA workspace -> host-layout outputs (x, l, L), tile transpose through shared memory
 void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg, const int32_t* cur,
                    const int32_t* perm, double* x_out, double* l_out, double* L_out, cudaStream_t st);

@@ -10,6 +10,7 @@
 #include "../../ratilqr.jl_b200/csrc/rl_components.cuh"
 #include "../../ratilqr.jl_b200/csrc/rl_coop.cuh"
 #include "../../ratilqr.jl_b200/csrc/rl_spec.cuh"
+#include "../../ratilqr.jl_b200/csrc/rl_coop2.cuh"
 #include "../../ratilqr.jl_b200/csrc/rl_host.hpp"
 
 #include "../../ratilqr.jl_b200/csrc/rl_user.cuh"
@@ -216,6 +217,27 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
     int rc2 = dispatch(desc->model_id, cost_id, [&](auto D, auto CT) {
       using DD = decltype(D);
       std::vector<double> traj(coop_traj_doubles(DD::n, DD::m, N));
+      if (g_coop == 2) {  // the two-warp speculative variant: the two "warps" of a round run one after the other
+        std::vector<double> tr2(coop2_traj_doubles(DD::n, DD::m, N));
+        for (size_t b = 0; b < B; ++b) {
+          const size_t p = b / (size_t)P.K;
+          if (P.active && !P.active[p]) continue;
+          CoopWs<DD::n, DD::m> w2[2];
+          Coop2Traj t;
+          t.n = DD::n; t.m = DD::m; t.N = N;
+          t.X = tr2.data(); t.U = t.X + (size_t)3 * (N + 1) * DD::n; t.Lg = t.U + (size_t)3 * N * DD::m; t.DL = t.Lg + (size_t)2 * N * DD::m * DD::n;
+          const double* cp = P.cost_params + (P.cp_count > 1 ? p * (size_t)P.ncp : 0);
+          SpecState S;
+          spec_state_init(P, S);
+          while (!S.done) {
+            SpecLaneRes res[2];
+            for (int g = 0; g < 2; ++g) res[g] = coop2_warp_work<DD, decltype(CT)>(0, g, P, S, cp, P.theta[b], p, w2[g], t);
+            spec_decide<2>(P, S, res, b, true);
+          }
+          coop2_write_outputs(P, t, S, b, 0, 1);
+        }
+        return;
+      }
       for (size_t b = 0; b < B; ++b) {
         CoopWs<DD::n, DD::m> w;
         CoopTraj tj;

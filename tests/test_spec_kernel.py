@@ -124,3 +124,51 @@ def test_spec_kernel_is_the_default_for_small_batches_and_matches_the_oracle(gpu
     assert np.max(np.abs(g["value"][ok] - o["value"][ok]) / np.abs(o["value"][ok])) < 1e-9
     for k in ("x", "l", "L"):
         assert np.max(np.abs(g[k][..., ok] - o[k][..., ok])) / np.max(np.abs(o[k][..., ok])) < 1e-9, k
+
+
+# ---- the two-warp speculative variant of the warp-cooperative kernel (csrc/rl_coop2.cuh) ---------------------------------
+def _coop_cases():
+    out = [c for c in _cases() if c[0] in ("c1", "c1_domain", "c2_epsmin", "restarts", "cartpole_dense")]
+    prob, x0, u = wl.c3_problem()
+    out.append(("c3_quadrotor", prob.spec(), x0, u, np.array([0.0, 0.005, 0.01, 0.02, 0.0234375, 0.05, 3.0]), None, None))
+    prob, x0, u = wl.c3_problem(N=7)
+    out.append(("c3_short_itermax", prob.spec(), x0, u, np.array([0.0, 0.01]), R.make_opts(iter_max=4, adaptive_eps_init=True), None))
+    return out
+
+
+@pytest.mark.parametrize("case", _coop_cases(), ids=lambda c: c[0])
+def test_coop2_bitwise_equals_one_warp_coop(hostemu_be, case):
+    _, spec, x0, u, th, opts, P = case
+    try:
+        hostemu_be.dll.hostemu_set_coop(2)
+        a = hostemu_be.ileqg_solve_batch(spec, x0, u, th, opts=opts, eps_hist_cap=64, P=P)
+        hostemu_be.dll.hostemu_set_coop(1)
+        b = hostemu_be.ileqg_solve_batch(spec, x0, u, th, opts=opts, eps_hist_cap=64, P=P)
+    finally:
+        hostemu_be.dll.hostemu_set_coop(0)
+    _same(a, b, 64)
+
+
+@pytest.mark.gpu
+def test_coop2_kernel_gpu_bitwise_equals_one_warp_coop(oracle_be):
+    """the CUDA library: quadrotor solves through the two-warp kernel (default for small batches) vs the one-warp kernel,
+    and both against the oracle"""
+    prob, x0, u = wl.c3_problem()
+    th = np.array([0.0, 0.005, 0.01, 0.02, 0.0234375, 0.05, 3.0])
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["RATILQR_COOP2"] = mode
+        try:
+            be = R.new_backend(0)
+            n0 = be.launch_count()
+            res[mode] = be.ileqg_solve_batch(prob.spec(), x0, u, th, eps_hist_cap=64)
+            assert be.launch_count() - n0 == 1   # one solve kernel, outputs written in host layout
+            be.close()
+        finally:
+            del os.environ["RATILQR_COOP2"]
+    _same(res["1"], res["0"], 64)
+    o = oracle_be.ileqg_solve_batch(prob.spec(), x0, u, th)
+    assert np.array_equal(res["1"]["status"], o["status"]) and np.array_equal(res["1"]["iters"], o["iters"])
+    ok = o["status"] == 0
+    assert np.max(np.abs(res["1"]["value"][ok] - o["value"][ok]) / np.abs(o["value"][ok])) < 1e-9
+    assert np.max(np.abs(res["1"]["L"][..., ok] - o["L"][..., ok])) / np.max(np.abs(o["L"][..., ok])) < 1e-9
