@@ -35,7 +35,22 @@ struct CoopWs {
   double x[n], u[m], xn[n], Sn[n * n], svn[n];
   double q, flag, nrm;  // stage cost value; domain-error flag; ||l - u||^2 of the rollout step
   double sc[8];         // per-stage trigonometry shared by the lanes (CoopDyn<quadrotor>)
+  double V[m * n], Hdlg[m];  // H L + G and H dl + g (dense stage)
+  // (i, j) of the t-th entry of the upper triangle of an n x n / m x m matrix, column by column (coop_ws_init)
+  unsigned char tn_i[n * (n + 1) / 2], tn_j[n * (n + 1) / 2], tm_i[m * (m + 1) / 2], tm_j[m * (m + 1) / 2];
 };
+
+// once per kernel: the index tables of the workspace
+template <int n, int m>
+RL_HD void coop_ws_init(int lane, CoopWs<n, m>& w) {
+  phase(lane, [&](int l) {
+    if (l != 0) return;
+    int t = 0;
+    for (int c = 0; c < n; ++c) for (int r = 0; r <= c; ++r) { w.tn_i[t] = (unsigned char)r; w.tn_j[t] = (unsigned char)c; ++t; }
+    t = 0;
+    for (int c = 0; c < m; ++c) for (int r = 0; r <= c; ++r) { w.tm_i[t] = (unsigned char)r; w.tm_j[t] = (unsigned char)c; ++t; }
+  });
+}
 
 // per-instance trajectories, contiguous per instance: X[2][(N+1)*n], U[2][N*m], Lg[N*m*n], DL[N*m]
 struct CoopTraj {
@@ -110,12 +125,254 @@ template <> struct CoopJac<Dyn<RATILQR_MODEL_QUADROTOR>> {
   }
 };
 
+// The lane's NE dot products of length LEN advance TOGETHER (k outer, fully unrolled): NE independent FMA chains per
+// lane and compile-time shared-memory offsets, instead of one rolled loop after the other.  get(q, k, a, b) yields the
+// k-th operand pair of output q; acc[q] is either started by the first product (start[q]) or accumulates onto its
+// initial value -- per output the same sequence of operations as rl::coldot / rl::coldot_acc / rl::dot_acc.
+template <int LEN, int NE, class Get>
+RL_HD void lane_dots(Get get, const bool* start, double* acc) {
+#pragma unroll
+  for (int k = 0; k < LEN; ++k) {
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      double a, b;
+      get(q, k, a, b);
+      acc[q] = (k == 0 && start[q]) ? a * b : rl_fma(a, b, acc[q]);
+    }
+  }
+}
+
+// One Riccati stage for a DENSE model (quadrotor, cart-pole: no compile-time structure of A, B), theta != 0, fused
+// accumulation: the arithmetic of coop_riccati_stage below, output element by output element, restructured for
+// instruction-level parallelism -- bit-identical results (tests/test_spec_kernel.py::test_coop_dense_stage...).
+template <class Tr, bool OPT, bool HAS_DL>
+RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, double mu, const double* RL_RESTRICT Winv,
+                                   double detW, double& s, double* detprod) {
+  constexpr int n = Tr::n, m = Tr::m;
+  phase(lane, [&](int l) {
+#pragma unroll
+    for (int q = 0; q < (n * n + 31) / 32; ++q) { const int e = l + 32 * q; if (e < n * n) w.M[e] = rl_fma(-theta, w.S[e], Winv[e]); }
+  });
+  // Cholesky in place, one column per step (as in coop_riccati_stage)
+  double detM = 1.0;
+  for (int j = 0; j < n; ++j) {
+    double d = w.M[j + j * n];
+    for (int k = 0; k < j; ++k) d = rl_fma(-w.M[j + k * n], w.M[j + k * n], d);
+    if (!(d > 0.0)) return 1;
+    detM = (j == 0) ? d : detM * d;
+    const double inv = rl_rsqrt(d);
+    phase(lane, [&](int l) {
+      if (l == 0) w.invd[j] = inv;
+      for (int i = j + 1 + l; i < n; i += 32) {
+        double a = w.M[j + i * n];
+        for (int k = 0; k < j; ++k) a = rl_fma(-w.M[i + k * n], w.M[j + k * n], a);
+        w.M[i + j * n] = a * inv;
+      }
+    });
+  }
+  // forward substitutions, column c of [S+ | s_vec+] per lane, kept in registers; right-looking: once Z[i] is known every
+  // later row takes its update at once (the updates of a row still arrive in increasing i: same rounding sequence)
+  phase(lane, [&](int l) {
+    if (l > n) return;
+    const int c = l;
+    double col[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) col[i] = (c < n) ? w.S[i + c * n] : w.sv[i];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const double zi = col[i] * w.invd[i];
+      col[i] = zi;
+#pragma unroll
+      for (int r = i + 1; r < n; ++r) col[r] = rl_fma(-w.M[r + i * n], zi, col[r]);
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) { if (c < n) w.Z[i + c * n] = col[i]; else w.z[i] = col[i]; }
+  });
+  // D S+ = S+ + theta Z'Z (every entry computed directly: products commute, so (i, j) and (j, i) get the same bits) and
+  // D s_vec+ = s_vec+ + theta Z'z
+  phase(lane, [&](int l) {
+    constexpr int TOT = n * n + n, NE = (TOT + 31) / 32;
+    const double* xa[NE]; const double* xb[NE]; double acc[NE]; bool start[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q, ee = e < TOT ? e : 0;
+      const int i = ee < n * n ? ee % n : ee - n * n, j = ee < n * n ? ee / n : 0;
+      xa[q] = w.Z + i * n; xb[q] = ee < n * n ? w.Z + j * n : w.z; acc[q] = 0.0; start[q] = true;
+    }
+    lane_dots<n, NE>([&](int q, int k, double& a, double& b) { a = xa[q][k]; b = xb[q][k]; }, start, acc);
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q;
+      if (e < n * n) w.DS[e] = rl_fma(theta, acc[q], w.S[(e % n) + (e / n) * n]);
+      else if (e < TOT) w.Dsv[e - n * n] = rl_fma(theta, acc[q], w.sv[e - n * n]);
+    }
+  });
+  double quad = w.z[0] * w.z[0];
+  for (int k = 1; k < n; ++k) quad = rl_fma(w.z[k], w.z[k], quad);
+  *detprod *= detW * detM;
+  const double extra = (theta / 2) * quad;
+  phase(lane, [&](int l) {  // T = (D S+) A, U = (D S+) B
+    constexpr int TOT = n * n + n * m, NE = (TOT + 31) / 32;
+    const double* xa[NE]; const double* xb[NE]; double acc[NE]; bool start[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q, ee = e < TOT ? e : 0;
+      const int f = ee < n * n ? ee : ee - n * n;
+      xa[q] = w.DS + f % n; xb[q] = (ee < n * n ? w.A : w.B) + (f / n) * n; acc[q] = 0.0; start[q] = true;
+    }
+    lane_dots<n, NE>([&](int q, int k, double& a, double& b) { a = xa[q][k * n]; b = xb[q][k]; }, start, acc);
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q;
+      if (e < n * n) w.T[e] = acc[q]; else if (e < TOT) w.U[e - n * n] = acc[q];
+    }
+  });
+  phase(lane, [&](int l) {  // g, G, H (upper triangle mirrored)
+    constexpr int NH = m * (m + 1) / 2, TOT = m + m * n + NH, NE = (TOT + 31) / 32;
+    const double* xa[NE]; const double* xb[NE]; double acc[NE]; bool start[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q, ee = e < TOT ? e : 0;
+      if (ee < m) { xa[q] = w.Dsv; xb[q] = w.B + ee * n; acc[q] = w.r[ee]; start[q] = false; }
+      else if (ee < m + m * n) {
+        const int f = ee - m, i = f % m, j = f / m;
+        xa[q] = w.T + j * n; xb[q] = w.B + i * n; start[q] = Tr::p_kind(i, j) == 0; acc[q] = start[q] ? 0.0 : w.Pm[f];
+      } else {
+        const int t = ee - m - m * n, i = w.tm_i[t], j = w.tm_j[t];
+        xa[q] = w.U + j * n; xb[q] = w.B + i * n; start[q] = Tr::r_kind(i, j) == 0; acc[q] = start[q] ? 0.0 : w.R[i + j * m];
+      }
+    }
+    lane_dots<n, NE>([&](int q, int k, double& a, double& b) { a = xa[q][k]; b = xb[q][k]; }, start, acc);
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q;
+      if (e < m) w.g[e] = acc[q];
+      else if (e < m + m * n) w.G[e - m] = acc[q];
+      else if (e < TOT) {
+        const int t = e - m - m * n, i = w.tm_i[t], j = w.tm_j[t];
+        const double h = (i == j) ? acc[q] + mu : acc[q];
+        w.H[i + j * m] = h;
+        w.H[j + i * m] = h;
+      }
+    }
+  });
+  if (OPT) {
+    for (int j = 0; j < m; ++j) {  // Cholesky of H, same column scheme
+      double d = w.H[j + j * m];
+      for (int k = 0; k < j; ++k) d = rl_fma(-w.CH[j + k * m], w.CH[j + k * m], d);
+      if (!(d > 0.0)) return 2;
+      const double inv = rl_rsqrt(d);
+      phase(lane, [&](int l) {
+        if (l == 0) w.invh[j] = inv;
+        for (int i = j + 1 + l; i < m; i += 32) {
+          double a = w.H[j + i * m];
+          for (int k = 0; k < j; ++k) a = rl_fma(-w.CH[i + k * m], w.CH[j + k * m], a);
+          w.CH[i + j * m] = a * inv;
+        }
+      });
+    }
+    phase(lane, [&](int l) {  // L = -H\G (column c per lane), dl = -H\g (column n)
+      if (l > n) return;
+      const int c = l;
+      double y[m];
+#pragma unroll
+      for (int i = 0; i < m; ++i) {
+        double a = (c < n) ? w.G[i + c * m] : w.g[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) a = rl_fma(-w.CH[i + k * m], y[k], a);
+        y[i] = a * w.invh[i];
+      }
+#pragma unroll
+      for (int i = m - 1; i >= 0; --i) {
+        double a = y[i];
+#pragma unroll
+        for (int k = i + 1; k < m; ++k) a = rl_fma(-w.CH[k + i * m], y[k], a);
+        y[i] = a * w.invh[i];
+      }
+#pragma unroll
+      for (int i = 0; i < m; ++i) { if (c < n) w.L[i + c * m] = -y[i]; else w.dl[i] = -y[i]; }
+    });
+  }
+  phase(lane, [&](int l) {  // V = H L + G, H dl, H dl + g
+    constexpr int TOT = m * n + (HAS_DL ? m : 0), NE = (TOT + 31) / 32;
+    const double* xa[NE]; const double* xb[NE]; double acc[NE]; bool start[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q, ee = e < TOT ? e : 0;
+      const int i = ee < m * n ? ee % m : ee - m * n;
+      xa[q] = w.H + i; xb[q] = ee < m * n ? w.L + (ee / m) * m : w.dl; acc[q] = 0.0; start[q] = true;
+    }
+    lane_dots<m, NE>([&](int q, int k, double& a, double& b) { a = xa[q][k * m]; b = xb[q][k]; }, start, acc);
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q;
+      if (e < m * n) { w.HL[e] = acc[q]; w.V[e] = acc[q] + w.G[e]; }
+      else if (e < TOT) { w.Hdl[e - m * n] = acc[q]; w.Hdlg[e - m * n] = acc[q] + w.g[e - m * n]; }
+    }
+  });
+  double sval = w.q + s;
+  if (HAS_DL) {
+    double a = w.dl[0] * w.Hdl[0];
+    for (int k = 1; k < m; ++k) a = rl_fma(w.dl[k], w.Hdl[k], a);
+    sval = dot_acc<m>(rl_fma(0.5, a, sval), w.dl, 1, w.g, 1);
+  }
+  s = sval + extra;
+  phase(lane, [&](int l) {  // s_vec and S (upper triangle, mirrored) into the double buffers
+    constexpr int NS = n * (n + 1) / 2, TOT = n + NS, NE = (TOT + 31) / 32;
+    const double* xa[NE]; const double* xb[NE]; double acc[NE]; bool start[NE]; int oi[NE], oj[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q, ee = e < TOT ? e : 0;
+      if (ee < n) { oi[q] = ee; oj[q] = -1; xa[q] = w.Dsv; xb[q] = w.A + ee * n; acc[q] = w.qv[ee]; start[q] = false; }
+      else {
+        const int t = ee - n, i = w.tn_i[t], j = w.tn_j[t];
+        oi[q] = i; oj[q] = j;
+        xa[q] = w.T + j * n; xb[q] = w.A + i * n; start[q] = Tr::q_kind(i, j) == 0; acc[q] = start[q] ? 0.0 : w.Q[i + j * n];
+      }
+    }
+    lane_dots<n, NE>([&](int q, int k, double& a, double& b) { a = xa[q][k]; b = xb[q][k]; }, start, acc);
+    bool cont[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) cont[q] = false;
+    // L'(H dl + g) resp. L'g for s_vec ; L'(H L + G) for S
+    lane_dots<m, NE>([&](int q, int k, double& a, double& b) {
+      a = w.L[k + oi[q] * m];
+      b = oj[q] < 0 ? (HAS_DL ? w.Hdlg[k] : w.g[k]) : w.V[k + oj[q] * m];
+    }, cont, acc);
+    // G'dl for s_vec (only with dl) ; G'L for S
+    lane_dots<m, NE>([&](int q, int k, double& a, double& b) {
+      a = w.G[k + oi[q] * m];
+      b = oj[q] < 0 ? (HAS_DL ? w.dl[k] : 0.0) : w.L[k + oj[q] * m];
+      if (oj[q] < 0 && !HAS_DL) a = 0.0;  // fma(0, 0, acc) == acc: the evaluating pass has no G'dl term
+    }, cont, acc);
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = l + 32 * q;
+      if (e < n) w.svn[e] = acc[q];
+      else if (e < TOT) { w.Sn[oi[q] + oj[q] * n] = acc[q]; w.Sn[oj[q] + oi[q] * n] = acc[q]; }
+    }
+  });
+  phase(lane, [&](int l) {
+#pragma unroll
+    for (int q = 0; q < (n * n + 31) / 32; ++q) { const int e = l + 32 * q; if (e < n * n) w.S[e] = w.Sn[e]; }
+    for (int e = l; e < n; e += 32) w.sv[e] = w.svn[e];
+  });
+  return 0;
+}
+
+#ifndef RL_COOP_DENSE
+#define RL_COOP_DENSE 1
+#endif
+
 // One Riccati stage, cooperative.  w.S / w.sv / s hold (S+, s_vec+, s+) on entry, the stage's values on exit.
 // returns 0 / 1 (M not PD) / 2 (H not PD); identical arithmetic per output element to rl::riccati_stage.
 template <class Tr, bool OPT, bool HAS_DL>
 RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, double mu, const double* RL_RESTRICT W,
                              const double* RL_RESTRICT Winv, double detW, double& s, double* detprod = nullptr) {
   constexpr int n = Tr::n, m = Tr::m;
+  if constexpr (RL_COOP_DENSE && RL_FUSED && !Tr::structured) {
+    if (theta != 0.0 && detprod) return coop_riccati_stage_dense<Tr, OPT, HAS_DL>(lane, w, theta, mu, Winv, detW, s, detprod);
+  }
   double extra = 0.0;
   if (theta == 0.0) {
     phase(lane, [&](int l) {
@@ -453,6 +710,7 @@ RL_HD bool coop_solve_instance(int lane, const SolveParams& P, size_t inst, Coop
   double mu = 0.0, delta = P.delta_0, d_current = rl_inf(), value = rl_inf();
   double eps_init = P.eps_init, eps = 0.0;
   bool init = true, need_opt = false;
+  coop_ws_init(lane, w);
   phase(lane, [&](int l) { for (int e = l; e < N * m * n; e += 32) tj.Lg[e] = 0.0; });  // initialize!: L = 0 (:230-232)
   {
     const double* x0 = P.x0 + (P.x0_count > 1 ? p * n : 0);

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(64) k_ileqg_solve_coop2(const __grid_constant_
   const double theta = P.theta[inst];
   SpecState S;
   spec_state_init(P, S);
+  coop_ws_init(lane, w);
   while (!S.done) {
     const SpecLaneRes r = coop2_warp_work<D, CT>(lane, g, P, S, cp, theta, p, w, t);
     if (lane == 0) res[g] = r;

@@ -229,6 +229,8 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
           const double* cp = P.cost_params + (P.cp_count > 1 ? p * (size_t)P.ncp : 0);
           SpecState S;
           spec_state_init(P, S);
+          coop_ws_init(0, w2[0]);
+          coop_ws_init(0, w2[1]);
           while (!S.done) {
             SpecLaneRes res[2];
             for (int g = 0; g < 2; ++g) res[g] = coop2_warp_work<DD, decltype(CT)>(0, g, P, S, cp, P.theta[b], p, w2[g], t);

@@ -172,3 +172,39 @@ def test_coop2_kernel_gpu_bitwise_equals_one_warp_coop(oracle_be):
     ok = o["status"] == 0
     assert np.max(np.abs(res["1"]["value"][ok] - o["value"][ok]) / np.abs(o["value"][ok])) < 1e-9
     assert np.max(np.abs(res["1"]["L"][..., ok] - o["L"][..., ok])) / np.max(np.abs(o["L"][..., ok])) < 1e-9
+
+
+def _dense_cases():
+    prob, x0, u = wl.c3_problem()
+    out = [("c3_quadrotor_diag_cost", prob.spec(), x0, u, np.array([0.0, 0.005, 0.01, 0.02, 0.0234375, 0.05, 3.0]), None)]
+    Q = np.diag([1.0] * 3 + [0.1] * 3 + [0.1] * 3 + [0.01] * 3)
+    Q[0, 1] = Q[1, 0] = 0.05
+    cost = R.QuadraticCost(12, 4, Q=Q, R=np.diag([0.01, 1.0, 1.0, 1.0]), Qf=10 * Q, xg=np.r_[1.0, 1.0, 1.0, np.zeros(9)], Pc=1e-3 * np.ones((12, 4)))
+    p2 = R.FiniteHorizonRiskSensitiveOptimalControlProblem(R.Quadrotor(0.05), cost.c, cost.h, R.ConstantCovariance(np.asarray(prob.W(0))), 20)
+    u2 = np.zeros((4, 20))
+    u2[0] = 9.81
+    out.append(("quadrotor_dense_cost", p2.spec(), np.zeros(12), u2, np.array([0.005, 0.01, 0.02]), R.make_opts(iter_max=8)))
+    cost = R.QuadraticCost(4, 1, Q=np.diag([0.1, 1.0, 0.01, 0.01]), R=np.array([[1e-3]]), Qf=10 * np.eye(4), xg=[0, np.pi, 0, 0], Pc=0.01 * np.ones((4, 1)))
+    p5 = R.FiniteHorizonRiskSensitiveOptimalControlProblem(R.CartPole(), cost.c, cost.h, R.ConstantCovariance(1e-4 * np.eye(4)), 25)
+    out.append(("cartpole", p5.spec(), np.zeros(4), 0.1 * np.ones((1, 25)), np.array([0.1, 0.3, 2.0]), R.make_opts(iter_max=15)))
+    return out
+
+
+@pytest.mark.parametrize("case", _dense_cases(), ids=lambda c: c[0])
+def test_coop_dense_stage_bitwise_equals_rolled_stage(hostemu_be, case):
+    """rl::coop_riccati_stage_dense (the lane's dot products advance together, right-looking substitution, full D S+) must
+    reproduce the plain element-by-element stage bit for bit: same operations per output element, only their interleaving
+    differs.  Reference build: the same emulation compiled with -DRL_COOP_DENSE=0."""
+    from tests import _hostemu
+    rolled = _hostemu.load_variant("hostemu_coop_rolled")
+    _, spec, x0, u, th, opts = case
+    try:
+        for be in (hostemu_be, rolled):
+            be.dll.hostemu_set_coop(1)
+        a = hostemu_be.ileqg_solve_batch(spec, x0, u, th, opts=opts, eps_hist_cap=64)
+        b = rolled.ileqg_solve_batch(spec, x0, u, th, opts=opts, eps_hist_cap=64)
+    finally:
+        for be in (hostemu_be, rolled):
+            be.dll.hostemu_set_coop(0)
+    assert np.any(b["status"] == 0)
+    _same(a, b, 64)
