@@ -153,22 +153,38 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
 #pragma unroll
     for (int q = 0; q < (n * n + 31) / 32; ++q) { const int e = l + 32 * q; if (e < n * n) w.M[e] = rl_fma(-theta, w.S[e], Winv[e]); }
   });
-  // Cholesky in place, one column per step (as in coop_riccati_stage)
+  // Cholesky in place, RIGHT-LOOKING: the upper triangle holds the running Schur complement, the lower triangle receives
+  // the factor.  Step j: every lane reads the pivot, scales the column entries it needs itself, and applies the rank-1
+  // update to its share of the trailing (k, i) entries (j < k <= i) -- one phase per step instead of a dependent chain of j
+  // FMAs per entry.  An entry still receives its updates in increasing j: the rounding sequence of the left-looking form.
   double detM = 1.0;
-  for (int j = 0; j < n; ++j) {
-    double d = w.M[j + j * n];
-    for (int k = 0; k < j; ++k) d = rl_fma(-w.M[j + k * n], w.M[j + k * n], d);
-    if (!(d > 0.0)) return 1;
-    detM = (j == 0) ? d : detM * d;
-    const double inv = rl_rsqrt(d);
-    phase(lane, [&](int l) {
-      if (l == 0) w.invd[j] = inv;
-      for (int i = j + 1 + l; i < n; i += 32) {
-        double a = w.M[j + i * n];
-        for (int k = 0; k < j; ++k) a = rl_fma(-w.M[i + k * n], w.M[j + k * n], a);
-        w.M[i + j * n] = a * inv;
-      }
-    });
+  {
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const double d = w.M[j + j * n];
+      if (!(d > 0.0)) { bad = 1; break; }
+      detM = (j == 0) ? d : detM * d;
+      const double inv = rl_rsqrt(d);
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int r = n - j - 1;                 // order of the trailing block
+      const int TOT = r * (r + 1) / 2;         // its upper-triangle entries
+      phase(lane, [&](int l) {
+        if (l == 0) w.invd[j] = inv;
+        if (l < r) w.M[(j + 1 + l) + j * n] = w.M[j + (j + 1 + l) * n] * inv;  // C[i, j], i = j + 1 + l
+#pragma unroll
+        for (int q = 0; q < (n * (n - 1) / 2 + 31) / 32; ++q) {
+          const int t = l + 32 * q;
+          if (t < TOT) {
+            const int k = j + 1 + w.tn_i[t], i = j + 1 + w.tn_j[t];
+            const double ci = w.M[j + i * n] * inv, ck = w.M[j + k * n] * inv;
+            w.M[k + i * n] = rl_fma(-ci, ck, w.M[k + i * n]);
+          }
+        }
+      });
+    }
+    if (bad) return 1;
   }
   // forward substitutions, column c of [S+ | s_vec+] per lane, kept in registers; right-looking: once Z[i] is known every
   // later row takes its update at once (the updates of a row still arrive in increasing i: same rounding sequence)
@@ -257,19 +273,27 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
     }
   });
   if (OPT) {
-    for (int j = 0; j < m; ++j) {  // Cholesky of H, same column scheme
-      double d = w.H[j + j * m];
-      for (int k = 0; k < j; ++k) d = rl_fma(-w.CH[j + k * m], w.CH[j + k * m], d);
-      if (!(d > 0.0)) return 2;
-      const double inv = rl_rsqrt(d);
-      phase(lane, [&](int l) {
-        if (l == 0) w.invh[j] = inv;
-        for (int i = j + 1 + l; i < m; i += 32) {
+    // Cholesky of H (m x m, tiny): every lane factors it redundantly in registers -- no phases, the same operations
+    double ch[m * m], ih[m];
+    {
+      int bad = 0;
+#pragma unroll
+      for (int j = 0; j < m; ++j) {
+        double d = w.H[j + j * m];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d = rl_fma(-ch[j + k * m], ch[j + k * m], d);
+        if (!(d > 0.0)) { bad = 1; break; }
+        const double inv = rl_rsqrt(d);
+        ih[j] = inv;
+#pragma unroll
+        for (int i = j + 1; i < m; ++i) {
           double a = w.H[j + i * m];
-          for (int k = 0; k < j; ++k) a = rl_fma(-w.CH[i + k * m], w.CH[j + k * m], a);
-          w.CH[i + j * m] = a * inv;
+#pragma unroll
+          for (int k = 0; k < j; ++k) a = rl_fma(-ch[i + k * m], ch[j + k * m], a);
+          ch[i + j * m] = a * inv;
         }
-      });
+      }
+      if (bad) return 2;
     }
     phase(lane, [&](int l) {  // L = -H\G (column c per lane), dl = -H\g (column n)
       if (l > n) return;
@@ -279,15 +303,15 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
       for (int i = 0; i < m; ++i) {
         double a = (c < n) ? w.G[i + c * m] : w.g[i];
 #pragma unroll
-        for (int k = 0; k < i; ++k) a = rl_fma(-w.CH[i + k * m], y[k], a);
-        y[i] = a * w.invh[i];
+        for (int k = 0; k < i; ++k) a = rl_fma(-ch[i + k * m], y[k], a);
+        y[i] = a * ih[i];
       }
 #pragma unroll
       for (int i = m - 1; i >= 0; --i) {
         double a = y[i];
 #pragma unroll
-        for (int k = i + 1; k < m; ++k) a = rl_fma(-w.CH[k + i * m], y[k], a);
-        y[i] = a * w.invh[i];
+        for (int k = i + 1; k < m; ++k) a = rl_fma(-ch[k + i * m], y[k], a);
+        y[i] = a * ih[i];
       }
 #pragma unroll
       for (int i = 0; i < m; ++i) { if (c < n) w.L[i + c * m] = -y[i]; else w.dl[i] = -y[i]; }
