@@ -407,8 +407,9 @@ def main():
             pass
         ach_gbs = byts / (ms_per_step * 1e-3) / 1e9
         # the exact configs[1] shape: ONE problem x 1024 theta (latency-bound: the speculative kernel, rl_spec.cuh)
-        s1, x01, u1, th1 = build_inputs(1, 0)
-        be.stage(s1, x01, u1, th1, P=1)
+        from ratilqr_b200 import workloads as wl1
+        p1, x01, u1 = wl1.c2_problem()
+        be.stage(p1.spec(), x01, u1, wl1.c2_thetas(THETAS))
         be.run(3)
         ms1 = be.run(args.steps) / args.steps
         nominal_tf = 148 * 64 * 2 * 1.965e9 / 1e12              # SMs x FP64 lanes x 2 flops x boost clock (B200 datasheet-level)
@@ -434,7 +435,7 @@ def main():
                             "flops_basis": "work summed over all ranks / slowest rank's time" if world > 1 else "this GPU"},
                "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
-               "c2_single": {"workload": "configs[1] exactly: 1 problem x 1024 theta", "ms_per_batch": ms1,
+               "c2_single": {"workload": "configs[1] exactly: 1 problem x 1024 theta (kernel only, CUDA events; speculative latency kernel)", "ms_per_batch": ms1,
                              "solves_per_sec": THETAS / (ms1 * 1e-3)},
                "mpc_step": {"workload": f"configs[4]: fleet of {Pf} independent RAT iLQR unicycle problems per GPU (CE: 10 theta x 5 "
                                         "iterations + final solve), ratilqr_ce_solve_fleet, host buffers in, theta_opt/value/l out",

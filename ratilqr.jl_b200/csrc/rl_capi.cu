@@ -347,6 +347,11 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   for (int i = 0; i < 8; ++i) P.mp[i] = i < desc->n_model_params ? desc->model_params[i] : 0.0;
   P.cost_params = ctx->d_cp.as<double>(); P.ncp = desc->n_cost_params; P.cp_count = desc->cost_params_count;
   P.W = ctx->d_W.as<double>(); P.Winv = ctx->d_Winv.as<double>(); P.detW = ctx->d_detW.as<double>(); P.W_tv = desc->W_time_varying;
+  P.w_const = (!desc->W_time_varying && n * n <= 36) ? 1 : 0;
+  if (P.w_const) {
+    for (int i = 0; i < n * n; ++i) { P.Wc[i] = wp.W[i]; P.Winvc[i] = wp.Winv[i]; }
+    P.detWc = wp.detW[0];
+  }
   P.x0 = ctx->d_x0.as<double>(); P.x0_count = in->x0_count;
   P.u_init = ctx->d_u.as<double>(); P.u_count = in->u_count;
   P.theta = ctx->d_theta.as<double>();
@@ -367,8 +372,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
     std::iota(ord.begin(), ord.end(), 0);
     const std::vector<int32_t>& key = ctx->fleet_key;
     std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return key[a] > key[b]; });
-    UP(ctx->d_order, ord.data(), (size_t)in->P * 4);
-    CU(cudaStreamSynchronize(ctx->stream));  // ord is a stack vector
+    UP(ctx->d_order, ord.data(), (size_t)in->P * 4);  // pageable source: cudaMemcpyAsync returns once it has been staged
     order = ctx->d_order.as<int32_t>();
   }
   if (!device_theta && rll::launch_sort_theta(P.theta, in->P, in->K, order, ctx->d_perm.as<int32_t>(), ctx->stream) == 0) {
@@ -501,8 +505,8 @@ static int apply_slot_order(ratilqr_ctx* ctx, const std::vector<int32_t>& key, i
   else std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] > key[b]; });
   for (int r = 0; r < P; ++r) for (int j = 0; j < K; ++j) perm[(size_t)r * K + j] = (int32_t)((size_t)order[r] * K + j);
   CU(ctx->d_perm.reserve(B * 4));
+  // (pageable source: the copy call returns once the vector has been staged for DMA, so it may go out of scope)
   CU(cudaMemcpyAsync(ctx->d_perm.p, perm.data(), B * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));  // perm is a stack vector
   ctx->sp.perm = ctx->d_perm.as<int32_t>();
   return 0;
 }
@@ -1410,8 +1414,7 @@ static int mpc_block(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, const r
   {
     std::vector<double> u0(m * N * P);
     for (int p = 0; p < P; ++p) memcpy(u0.data() + (size_t)p * m * N, u_init + (u_count > 1 ? (size_t)p * m * N : 0), m * N * 8);
-    UP(ctx->d_u, u0.data(), u0.size() * 8);
-    CU(cudaStreamSynchronize(st));  // u0 is a stack vector
+    UP(ctx->d_u, u0.data(), u0.size() * 8);  // pageable source: staged before the call returns
   }
   CU(ctx->d_mpc[0].reserve(n * (steps + 1) * P * 8)); CU(ctx->d_mpc[1].reserve(m * steps * P * 8));
   CU(ctx->d_mpc[2].reserve(steps * P * 8)); CU(ctx->d_mpc[3].reserve(steps * P * 8));

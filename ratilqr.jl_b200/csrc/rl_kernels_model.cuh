@@ -13,15 +13,16 @@ namespace rll {
 using namespace rl;
 
 // ---- the hot kernel: one persistent thread per iLEQG instance (solve!, ileqg.jl:635-659) ------------------------
-template <class D, class CT, int THREADS, int MINB>
+// WC: W(k) is constant and small: inv(W) is read from the argument block (constant bank), see SolveParams::Winvc
+template <class D, class CT, int THREADS, int MINB, bool WC = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_ileqg_solve(const __grid_constant__ SolveParams P) {
   extern __shared__ double stage_area[];  // [2][RL_STAGE_NV][THREADS] doubles when staging is enabled, else empty
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   Stage sg;
   sg.base = (UseStage<D>::value && P.use_stage) ? stage_area + threadIdx.x : nullptr;
   sg.stride = THREADS;
-  if (P.queue) solve_dynamic<D, CT>(P, b, sg);  // persistent: every thread keeps pulling instances
-  else if (b < (size_t)P.B) solve_instance<D, CT>(P, b, sg);
+  if (!WC && P.queue) solve_dynamic<D, CT>(P, b, sg);  // persistent: every thread keeps pulling instances
+  else if (b < (size_t)P.B) solve_instance<D, CT, WC>(P, b, sg);
 }
 
 // ---- rollouts / cost / linearize: thread = instance (host layout, instance slowest) ----------

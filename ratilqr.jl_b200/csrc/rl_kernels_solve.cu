@@ -20,7 +20,7 @@ namespace rll {
 
 using namespace rl;
 
-template <class D, class CT, int THREADS, int MINB>
+template <class D, class CT, int THREADS, int MINB, bool WC = false>
 static void launch_shape(const SolveParams& P, cudaStream_t st) {
   int blocks = (P.B + THREADS - 1) / THREADS;
   const size_t smem = UseStage<D>::value ? (size_t)2 * RL_STAGE_NV * THREADS * sizeof(double) : 0;
@@ -33,7 +33,7 @@ static void launch_shape(const SolveParams& P, cudaStream_t st) {
   bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     configured = true;
-    auto kfn = k_ileqg_solve<D, CT, THREADS, MINB>;
+    auto kfn = k_ileqg_solve<D, CT, THREADS, MINB, WC>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (smem > 0) {
       // the default L1/shared split admits only a few staging CTAs per SM: ask for what MINB resident CTAs need
@@ -50,7 +50,7 @@ static void launch_shape(const SolveParams& P, cudaStream_t st) {
     }
   }
   if (P.queue && blocks > resident * sms) blocks = resident * sms;  // persistent grid: exactly one resident wave
-  k_ileqg_solve<D, CT, THREADS, MINB><<<blocks, THREADS, smem, st>>>(P);
+  k_ileqg_solve<D, CT, THREADS, MINB, WC><<<blocks, THREADS, smem, st>>>(P);
 }
 
 // launch shape = (threads per CTA, min resident CTAs per SM => register cap).  The default was chosen from
@@ -76,7 +76,12 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
         // thread): 7.3 vs 8.2 ms for 10-1024 solves, 39 vs 43 ms for a 56,830-instance CE round, equal at 82k
         // (profiles/r01_shape_vs_batch.jsonl).
         static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
-        if ((size_t)P.B <= (size_t)sms * 384 && !P.queue) launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4>(P, st);  // + constants pinned in L1
+        static const bool wc_on = [] { const char* e = getenv("RATILQR_WCONST"); return !(e && e[0] == '0'); }();  // A/B runs
+        const bool wc = wc_on && P.w_const && !P.queue;  // constant W: inv(W) from the constant bank
+        if ((size_t)P.B <= (size_t)sms * 384 && !P.queue) {
+          if (wc) launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4, true>(P, st);
+          else launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4>(P, st);  // + constants pinned in L1
+        } else if (wc) launch_shape<D, CT, 128, 3, true>(P, st);
         else launch_shape<D, CT, 128, 3>(P, st);   // best of the sweeps in profiles/r01_tune_*.jsonl
         return;
       }
