@@ -76,8 +76,10 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
         // thread): 7.3 vs 8.2 ms for 10-1024 solves, 39 vs 43 ms for a 56,830-instance CE round, equal at 82k
         // (profiles/r01_shape_vs_batch.jsonl).
         static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
-        static const bool wc_on = [] { const char* e = getenv("RATILQR_WCONST"); return !(e && e[0] == '0'); }();  // A/B runs
-        const bool wc = wc_on && P.w_const && !P.queue;  // constant W: inv(W) from the constant bank
+        // inv(W) from the constant bank instead of L1: measured 0.8 % SLOWER at full load (4.67 vs 4.71 M solves/s, same box,
+        // two alternating runs each: profiles/r02_wconst_ab.txt) and equal in the latency regime, so it stays opt-in
+        static const bool wc_on = [] { const char* e = getenv("RATILQR_WCONST"); return e && e[0] == '1'; }();
+        const bool wc = wc_on && P.w_const && !P.queue;
         if ((size_t)P.B <= (size_t)sms * 384 && !P.queue) {
           if (wc) launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4, true>(P, st);
           else launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4>(P, st);  // + constants pinned in L1
