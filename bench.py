@@ -106,9 +106,15 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+DISTINCT_FLEETS = False  # --distinct-fleets: every rank draws its own problems (round-1 behaviour: +-5 % work per rank)
+
+
 def build_inputs(P, rank):
+    """Weak scaling with EQUAL per-GPU work: every rank owns the same P problem definitions (x0, goal) and its own theta
+    populations.  The iterations a solve needs are a property of the problem far more than of theta, so ranks that draw
+    their own problems differ by +-5 % in work and the job is timed by the heaviest draw (round 1: 410 vs 384 ms)."""
     from ratilqr_b200 import workloads as wl
-    prob, cps, x0, u = wl.fleet(P, key=7 + 1000 * rank)
+    prob, cps, x0, u = wl.fleet(P, key=7 + (1000 * rank if DISTINCT_FLEETS else 0))
     theta = np.concatenate([wl.positive_thetas(THETAS, key=20201028 + p + 100000 * rank) for p in range(P)])
     return prob.spec(cost_params=cps), x0, u, theta
 
@@ -241,8 +247,11 @@ def main():
     ap.add_argument("--fleet-problems", type=int, default=8192, help="RAT iLQR problems per GPU for the MPC-step figure")
     ap.add_argument("--cpu-sample-problems", type=int, default=0, help="problems per CPU step; 0 = 8 per step for the reference arm (a different selection every step), 48 for the in-run baseline")
     ap.add_argument("--no-latency-cases", action="store_true")
+    ap.add_argument("--distinct-fleets", action="store_true", help="every rank draws its own problems instead of the same problem set with its own theta populations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global DISTINCT_FLEETS
+    DISTINCT_FLEETS = args.distinct_fleets
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,6 +261,8 @@ def main():
               "solves_per_step_per_gpu": args.problems * THETAS, "kl_bound": 0.1,
               "l2_policy": f"inputs_larger_than_l2 ({args.problems * THETAS * 8864 / 1e6:.0f} MB SoA workspace per step vs 126 MB L2)",
               "parallelism": f"dp{world}",
+              "rank_inputs": ("every rank draws its own problems and theta populations" if args.distinct_fleets else
+                              "every rank owns the same problem definitions with its own theta populations (equal per-GPU work)"),
               "slot_order": ("natural" if args.no_profile_warm else
                              "problems heaviest-first by the iterations a previous call (different theta population) needed")}
     config.pop("model")
@@ -362,7 +373,7 @@ def main():
     #      CE defaults 10 theta x 5 iterations + final solve, whole loop on the device, host buffers in/out) ----------
     Pf = args.fleet_problems
     from ratilqr_b200 import workloads as wl
-    fprob, fcps, fx0, fu = wl.fleet(Pf, key=70 + rank)
+    fprob, fcps, fx0, fu = wl.fleet(Pf, key=70 + (rank if args.distinct_fleets else 0))
     fspec = fprob.spec(cost_params=fcps)
     be.ce_solve_fleet(fspec, fx0, fu, 0.1, 1.0, 2.0, seed=7 + rank, want=())  # warm-up (allocations)
     fleet_all = []
@@ -425,15 +436,16 @@ def main():
                "clocks": clocks, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "api": "ratilqr_ce_costs (compute_cost), host buffers in, cost+status vectors out; a fresh theta population per step"},
-               "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+               "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf * world, "unit": "TFLOP/s", "frac": ach_tf / (peak_tf * world),
+                            "peak_per_gpu": peak_tf,
                             "traffic": traffic, "algorithmic_bytes_per_launch": byts, "kernel": "k_ileqg_solve<unicycle, quadratic>",
                             "peak_source": "burst DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 figure)",
-                            "peak_sustained": peak_sus, "frac_of_sustained": ach_tf / peak_sus,
-                            "peak_nominal": nominal_tf, "frac_of_nominal": ach_tf / nominal_tf,
-                            "peak_at_measured_clock": clock_tf, "frac_of_peak_at_measured_clock": ach_tf / clock_tf,
+                            "peak_sustained": peak_sus * world, "frac_of_sustained": ach_tf / (peak_sus * world),
+                            "peak_nominal": nominal_tf * world, "frac_of_nominal": ach_tf / (nominal_tf * world),
+                            "peak_at_measured_clock": clock_tf * world, "frac_of_peak_at_measured_clock": ach_tf / (clock_tf * world),
                             "flops_per_launch": flops,
                             "flops_basis": "work summed over all ranks / slowest rank's time" if world > 1 else "this GPU"},
-               "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+               "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak * world, "unit": "GB/s", "frac": ach_gbs / (hbm_peak * world),
                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
                "c2_single": {"workload": "configs[1] exactly: 1 problem x 1024 theta (kernel only, CUDA events; speculative latency kernel)", "ms_per_batch": ms1,
                              "solves_per_sec": THETAS / (ms1 * 1e-3)},
