@@ -146,3 +146,74 @@ def test_whole_solves_match_literal(named_backend, tag):
         assert np.allclose(r["eps_hist"][1, :nt, i], eh[:, 1], rtol=0, atol=1e3 * tol * abs(float(g("value")))), (tag, th)
         # the float64 statement of the reference walks the same discrete path
         assert int(z[f"f64/{i}/iters"]) == int(g("iters")) and int(z[f"f64/{i}/trials"]) == int(g("trials"))
+
+
+# ---- live comparison (no fixtures): the float64 literal statement of ileqg.jl vs every CPU provider on random problems ----
+_LIT_MODELS = {1: "single_integrator", 2: "power_law", 3: "double_integrator", 4: "pendulum", 5: "cartpole", 6: "unicycle"}
+
+
+def _literal_solve(spec, x0, u, theta, opts):
+    from tests.ref_literal import ileqg_literal as lit
+    LA = lit.F64
+    n, m, N = spec.n, spec.m, spec.N
+    f = lit.make_dynamics(LA, _LIT_MODELS[spec.model_id], list(spec.model_params))
+    c, h = lit.make_quadratic_cost(LA, n, m, list(spec.cost_params))
+    W = LA.arr(np.asarray(spec.W).reshape(n, n, order="F"))
+    prob = lit.Problem(f, c, h, lambda k: W, N, n, m)
+    sol = lit.Solver(LA, **opts)
+    try:
+        x, l, L, v, eh = lit.solve(LA, sol, prob, x0, [u[:, k] for k in range(N)], theta)
+    except lit.NotPosDef:
+        return None
+    return dict(x=np.stack(x, -1), l=np.stack(l, -1), L=np.stack(L, -1), value=float(v), iters=sol.iter_current, trials=len(eh),
+                restarts=sol.restarts)
+
+
+def _random_problem(rng, which):
+    def spd(k, scale):
+        G = rng.standard_normal((k, k))
+        return scale * (G @ G.T / k + 0.3 * np.eye(k))
+    if which == "single":
+        f, n, m, N = R.SingleIntegrator(0.5), 2, 2, 8
+    elif which == "double":
+        f, n, m, N = R.DoubleIntegrator(0.2), 4, 2, 10
+    elif which == "pendulum":
+        f, n, m, N = R.Pendulum(), 2, 1, 12
+    elif which == "cartpole":
+        f, n, m, N = R.CartPole(), 4, 1, 10
+    else:
+        f, n, m, N = R.Unicycle(0.1), 4, 2, 10
+    # dense Q, R, Qf, a cross term Pc and a time-scaled stage weight: everything QuadraticCost can express
+    cost = R.QuadraticCost(n, m, Q=spd(n, 0.5), R=spd(m, 0.3), Qf=spd(n, 2.0), xg=rng.standard_normal(n), Pc=0.05 * rng.standard_normal((n, m)),
+                           ws0=1.0, ws1=float(rng.uniform(0.0, 0.2)), c0=0.1, c1=0.01, h0=0.5)
+    prob = R.FiniteHorizonRiskSensitiveOptimalControlProblem(f, cost.c, cost.h, R.ConstantCovariance(spd(n, 0.02)), N)
+    return prob, 0.3 * rng.standard_normal(n), 0.1 * rng.standard_normal((m, N))
+
+
+@pytest.mark.parametrize("which", ["single", "double", "pendulum", "cartpole", "unicycle"])
+def test_random_problems_match_literal_float64(which, oracle_be, hostemu_be):
+    """dense random quadratic costs (non-diagonal Q, R, cross term, time-scaled weight), dense random W, five registered
+    models, theta from 0 to beyond breakdown: oracle and kernel arithmetic (g++ build) against the literal float64
+    statement of ileqg.jl evaluated live -- same discrete path, 1e-9 on values / trajectories / gains"""
+    rng = np.random.Generator(np.random.Philox(key=77 + ["single", "double", "pendulum", "cartpole", "unicycle"].index(which)))
+    opts = dict(iter_max=12)
+    checked = feasible = 0
+    for _ in range(4):
+        prob, x0, u = _random_problem(rng, which)
+        spec = prob.spec()
+        thetas = np.array([0.0, 0.02, 0.15, 1.0, 40.0])
+        res = [be.ileqg_solve_batch(spec, x0, u, thetas, opts=R.make_opts(**opts)) for be in (oracle_be, hostemu_be)]
+        for i, th in enumerate(thetas):
+            ref = _literal_solve(spec, x0, u, float(th), opts)
+            for r in res:
+                if ref is None:
+                    assert r["status"][i] in (1, 2), (which, th, r["status"][i])
+                    continue
+                assert r["status"][i] == 0, (which, th)
+                assert r["iters"][i] == ref["iters"] and r["trials"][i] == ref["trials"] and r["restarts"][i] == ref["restarts"], (which, th)
+                assert abs(r["value"][i] - ref["value"]) <= 1e-9 * abs(ref["value"]) + 1e-12
+                for k in ("x", "l", "L"):
+                    assert _relerr(r[k][..., i], ref[k]) < 1e-9, (which, th, k)
+            checked += 1
+            feasible += ref is not None
+    assert checked == 20 and feasible >= 5
