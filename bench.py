@@ -396,6 +396,12 @@ def main():
     barrier()
     mc_s = max_over_ranks(time.perf_counter() - t0)
     mc_finite = sum_over_ranks(float(np.isfinite(mc["stats"][:, 0]).sum()))
+    # the receding-horizon driver: 4 consecutive MPC steps of the same fleet without leaving the device (plan, true-system
+    # step with Philox disturbances, plan shift: ratilqr_mpc_fleet_run); steps after the first are warm-started
+    barrier()
+    mr = be.mpc_fleet_run(fspec, fx0, fu, 4, 0.1, 1.0, 2.0, seed=7 + rank, noise_seed=13 + rank)
+    barrier()
+    mpc_dev_ms = [max_over_ranks(float(t)) for t in mr["ms"]]
 
     out = None
     if rank == 0:
@@ -454,6 +460,8 @@ def main():
                             "ms_per_fleet_step": fleet_s * 1e3, "ms_all": [t * 1e3 for t in fleet_all], "problems_per_sec": Pf * world / fleet_s,
                             "us_per_problem_step": fleet_s * 1e6 / (Pf * world), "ce_rounds": fr["rounds"],
                             "final_solves_ok": int(fleet_ok), "problems": Pf * world,
+                            "on_device_driver_ms_per_step": mpc_dev_ms,
+                            "on_device_driver": "ratilqr_mpc_fleet_run, 4 receding-horizon steps (cold start, then warm-started by the shifted plans)",
                             "mc_eval": {"samples_per_problem": MC, "ms": mc_s * 1e3, "rollouts_per_sec": MC * Pf * world / mc_s,
                                         "problems_with_finite_mean": int(mc_finite),
                                         "call": "ratilqr_mc_rollout, host policy buffers in, J + stats out, Philox noise"}}}

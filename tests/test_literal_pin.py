@@ -190,6 +190,13 @@ def _random_problem(rng, which):
     return prob, 0.3 * rng.standard_normal(n), 0.1 * rng.standard_normal((m, N))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["single", "double", "pendulum", "cartpole", "unicycle"])
+def test_random_problems_match_literal_float64_gpu(which, gpu_be):
+    """the same live comparison for the CUDA library (speculative latency kernel: these are small batches)"""
+    test_random_problems_match_literal_float64(which, gpu_be, gpu_be)
+
+
 @pytest.mark.parametrize("which", ["single", "double", "pendulum", "cartpole", "unicycle"])
 def test_random_problems_match_literal_float64(which, oracle_be, hostemu_be):
     """dense random quadratic costs (non-diagonal Q, R, cross term, time-scaled weight), dense random W, five registered
