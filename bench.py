@@ -403,6 +403,27 @@ def main():
     barrier()
     mpc_dev_ms = [max_over_ranks(float(t)) for t in mr["ms"]]
 
+    # ---- the path's one real exchange step at scale: ONE problem's 65,536-theta population sharded over the ranks, the cost
+    #      vector all-gathered on device buffers inside the library (ratilqr_ce_costs_sharded); N = 1: plain ratilqr_ce_costs
+    from ratilqr_b200 import distributed as D_
+    pp, px0, pu = wl.c2_problem()
+    big_theta = wl.positive_thetas(65536, key=65536)
+    sharded = None
+    try:
+        D_.sharded_ce_costs(be, pp.spec(), px0, pu, big_theta, 0.1)  # warm-up: attaches the library's communicator, allocations
+        ts = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            big_cost = D_.sharded_ce_costs(be, pp.spec(), px0, pu, big_theta, 0.1)
+            barrier()
+            ts.append(max_over_ranks(time.perf_counter() - t0))
+        sharded = {"workload": "configs[1]'s problem with a 65,536-theta population, block-sharded over the ranks; one in-library "
+                               "ncclAllGather of (value, status) on device buffers; every rank ends up with the whole cost vector",
+                   "thetas": 65536, "ms": min(ts) * 1e3, "solves_per_sec": 65536 / min(ts), "finite_costs": int(np.isfinite(big_cost).sum())}
+    except Exception as e:  # noqa: BLE001  (secondary figure: never take the headline down with it)
+        sharded = {"error": str(e)[:200]}
+
     out = None
     if rank == 0:
         peak_tf = be.fp64_probe()
@@ -465,6 +486,7 @@ def main():
                             "mc_eval": {"samples_per_problem": MC, "ms": mc_s * 1e3, "rollouts_per_sec": MC * Pf * world / mc_s,
                                         "problems_with_finite_mean": int(mc_finite),
                                         "call": "ratilqr_mc_rollout, host policy buffers in, J + stats out, Philox noise"}}}
+        out["sharded_population"] = sharded
         if per_rank is not None:
             out["per_rank"] = per_rank
         if latency is not None:
