@@ -56,7 +56,7 @@ struct ratilqr_ctx {
   int coop_cost_id = 0;
   DBuf d_coop_traj;
   rl::SolveParams sp;
-  DBuf d_cp, d_W, d_Winv, d_detW, d_x0, d_u, d_theta, d_X, d_U, d_Lg, d_DL;
+  DBuf d_cp, d_W, d_Winv, d_detW, d_x0, d_u, d_theta, d_X;
   DBuf d_value, d_status, d_iters, d_trials, d_restarts, d_mu, d_d, d_cur, d_eps, d_perm;
   DBuf d_out1, d_out2, d_out3;  // host-layout staging for x, l, L
   // user-extensible device models (NVRTC): id = RATILQR_MODEL_USER_BASE + index
@@ -323,10 +323,8 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   const size_t cols = ctx->spec_G ? B * ctx->spec_G : B;  // workspace columns: one per thread
   const size_t pol = ctx->spec_G ? 2 : 1;                 // the speculative kernel double-buffers the policy (Lg, DL)
   const size_t Bp = (cols + 31) / 32 * 32;  // the workspace is tiled in groups of 32 thread slots
-  CU(ctx->d_X.reserve(2 * (size_t)(N + 1) * n * Bp * 8));
-  CU(ctx->d_U.reserve(2 * (size_t)N * m * Bp * 8));
-  CU(ctx->d_Lg.reserve(pol * (size_t)N * m * n * Bp * 8));
-  CU(ctx->d_DL.reserve(pol * (size_t)N * m * Bp * 8));
+  const rl::WsLayout wl = rl::ws_layout(n, m, N, (int)pol);  // one allocation of per-tile records (rl::SolveParams::X)
+  CU(ctx->d_X.reserve(wl.rec * Bp * 8));
   CU(ctx->d_value.reserve(B * 8));
   CU(ctx->d_mu.reserve(B * 8));
   CU(ctx->d_d.reserve(B * 8));
@@ -340,7 +338,8 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
     CU(cudaMemsetAsync(ctx->d_eps.p, 0, B * eps_cap * 16, ctx->stream));
   }
   // gains of instances that fail before their first optimising pass stay zero (initialize!: L = 0)
-  if (!ctx->spec_G) CU(cudaMemsetAsync(ctx->d_Lg.p, 0, (size_t)N * m * n * Bp * 8, ctx->stream));
+  if (!ctx->spec_G)
+    CU(cudaMemset2DAsync(ctx->d_X.as<double>() + wl.oLg * 32, wl.rec * 32 * 8, 0, (size_t)N * m * n * 32 * 8, Bp / 32, ctx->stream));
   rl::SolveParams& P = ctx->sp;
   memset(&P, 0, sizeof(P));
   P.N = N; P.B = (int)B; P.K = in->K;
@@ -357,7 +356,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   P.theta = ctx->d_theta.as<double>();
   P.mu_min = opts->mu_min; P.delta_0 = opts->delta_0; P.lambda = opts->lambda; P.d = opts->d;
   P.iter_max = opts->iter_max; P.eps_auto = opts->adaptive_eps_init; P.eps_init = opts->eps_init; P.eps_min = opts->eps_min;
-  P.X = ctx->d_X.as<double>(); P.U = ctx->d_U.as<double>(); P.Lg = ctx->d_Lg.as<double>(); P.DL = ctx->d_DL.as<double>();
+  P.X = ctx->d_X.as<double>(); P.U = P.X + wl.oU * 32; P.Lg = P.X + wl.oLg * 32; P.DL = P.X + wl.oDL * 32; P.rec = wl.rec;
   P.value = ctx->d_value.as<double>(); P.status = ctx->d_status.as<int32_t>(); P.iters = ctx->d_iters.as<int32_t>();
   P.trials = ctx->d_trials.as<int32_t>(); P.restarts = ctx->d_restarts.as<int32_t>();
   P.mu_out = ctx->d_mu.as<double>(); P.d_out = ctx->d_d.as<double>(); P.cur = ctx->d_cur.as<int32_t>();
@@ -536,7 +535,7 @@ static int device_plan(ratilqr_ctx* ctx, const double** plan) {
   }
   const size_t B = (size_t)ctx->B;
   CU(ctx->d_out2.reserve((size_t)ctx->m * ctx->N * B * 8));
-  rll::launch_gather(ctx->n, ctx->m, ctx->N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.cur, ctx->sp.perm, nullptr,
+  rll::launch_gather(ctx->n, ctx->m, ctx->N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.rec, ctx->sp.cur, ctx->sp.perm, nullptr,
                      ctx->d_out2.as<double>(), nullptr, ctx->stream);
   if (int rc = check_launch(ctx, "k_gather")) return rc;
   *plan = ctx->d_out2.as<double>();
@@ -561,7 +560,7 @@ static int fetch_internal(ratilqr_ctx* ctx, ratilqr_ileqg_out* out) {
       FAIL(-4, "trajectories were not retained by this staged solve: request them through ratilqr_ileqg_solve_batch");
     dx = out->x ? ctx->sp.xo : nullptr; dl = out->l ? ctx->sp.lo : nullptr; dL = out->L ? ctx->sp.Lo : nullptr;
   } else if (dx || dl || dL) {
-    rll::launch_gather(n, m, N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.cur, ctx->sp.perm, dx, dl, dL, st);
+    rll::launch_gather(n, m, N, (int)B, ctx->sp.X, ctx->sp.U, ctx->sp.Lg, ctx->sp.rec, ctx->sp.cur, ctx->sp.perm, dx, dl, dL, st);
     if (int rc = check_launch(ctx, "k_gather", (dx ? 1 : 0) + (dl ? 1 : 0) + (dL ? 1 : 0))) return rc;
   }
 #define DOWN(dst, src, bytes) if (dst) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))
@@ -622,7 +621,7 @@ int32_t ratilqr_destroy(ratilqr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DBuf* all[] = {&ctx->d_cp, &ctx->d_W, &ctx->d_Winv, &ctx->d_detW, &ctx->d_x0, &ctx->d_u, &ctx->d_theta, &ctx->d_X,
-                 &ctx->d_U, &ctx->d_Lg, &ctx->d_DL, &ctx->d_value, &ctx->d_status, &ctx->d_iters, &ctx->d_trials,
+                 &ctx->d_value, &ctx->d_status, &ctx->d_iters, &ctx->d_trials,
                  &ctx->d_restarts, &ctx->d_mu, &ctx->d_d, &ctx->d_cur, &ctx->d_eps, &ctx->d_perm, &ctx->d_out1, &ctx->d_out2,
                  &ctx->d_out3, &ctx->d_cost, &ctx->d_coop_traj, &ctx->d_queue};
   for (DBuf* b : all) b->release();

@@ -22,7 +22,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_ileqg_solve(const __grid_cons
   sg.base = (UseStage<D>::value && P.use_stage) ? stage_area + threadIdx.x : nullptr;
   sg.stride = THREADS;
   if (!WC && P.queue) solve_dynamic<D, CT>(P, b, sg);  // persistent: every thread keeps pulling instances
-  else if (b < (size_t)P.B) solve_instance<D, CT, WC>(P, b, sg);
+  else if (b < (size_t)P.B) {
+    if (sg.base) solve_instance<D, CT, WC, 1>(P, b, sg);
+    else solve_instance<D, CT, WC, 0>(P, b, sg);
+  }
 }
 
 // ---- rollouts / cost / linearize: thread = instance (host layout, instance slowest) ----------

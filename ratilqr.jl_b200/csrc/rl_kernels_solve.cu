@@ -178,10 +178,10 @@ int launch_solve(int model_id, int cost_id, const SolveParams& P, cudaStream_t s
 
 // ---- outputs: warp-tiled SoA workspace -> host layout -------------------------------------------
 // src element e of the instance in slot b: src[((b/32) * Etot + buf_b * E + e) * 32 + b%32]  (buf_b = cur[b] for the
-// double-buffered arrays, Etot = elements per instance of the whole array).  dst: dst[instance * E + e].
+// double-buffered arrays, Etot = elements per slot of the whole workspace record).  dst: dst[instance * E + e].
 // 32x32 tiles through shared memory: coalesced on both sides.
 __global__ void k_gather(const double* __restrict__ src, const int32_t* __restrict__ cur,
-                         const int32_t* __restrict__ perm, int E, int Etot, int B, double* __restrict__ dst) {
+                         const int32_t* __restrict__ perm, int E, size_t Etot, int B, double* __restrict__ dst) {
   __shared__ double tile[32][33];
   int b0 = blockIdx.x * 32, e0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -198,12 +198,12 @@ __global__ void k_gather(const double* __restrict__ src, const int32_t* __restri
   }
 }
 
-void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg,
+void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg, size_t rec,
                    const int32_t* cur, const int32_t* perm, double* x_out, double* l_out, double* L_out, cudaStream_t st) {
   dim3 th(32, 8);
-  if (x_out) { int E = n * (N + 1); k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(X, cur, perm, E, 2 * E, B, x_out); }
-  if (l_out) { int E = m * N; k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(U, cur, perm, E, 2 * E, B, l_out); }
-  if (L_out) { int E = m * n * N; k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(Lg, nullptr, perm, E, E, B, L_out); }
+  if (x_out) { int E = n * (N + 1); k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(X, cur, perm, E, rec, B, x_out); }
+  if (l_out) { int E = m * N; k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(U, cur, perm, E, rec, B, l_out); }
+  if (L_out) { int E = m * n * N; k_gather<<<dim3((B + 31) / 32, (E + 31) / 32), th, 0, st>>>(Lg, nullptr, perm, E, rec, B, L_out); }
 }
 
 // ---- theta sort: one CTA per problem, bitonic sort of (theta, index) in shared memory ---------------

@@ -27,7 +27,8 @@ size_t coop2_smem_query(int model_id, int cost_id, int N);
 int launch_solve_coop2(int model_id, int cost_id, const rl::SolveParams& P, cudaStream_t st);
 
 // SoA workspace -> host-layout outputs (x, l, L), tile transpose through shared memory
-void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg, const int32_t* cur,
+// (X, U, Lg: sections of the tiled workspace, `rec` = elements per slot record, see rl::SolveParams)
+void launch_gather(int n, int m, int N, int B, const double* X, const double* U, const double* Lg, size_t rec, const int32_t* cur,
                    const int32_t* perm, double* x_out, double* l_out, double* L_out, cudaStream_t st);
 
 // per-problem ascending sort of theta -> slot-to-instance permutation, problems laid out in `order` (device, P entries,

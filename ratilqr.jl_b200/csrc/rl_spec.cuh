@@ -50,10 +50,10 @@ struct SpecCols {
   const SolveParams* P;
   size_t tile, lane0;  // warp tile of the group, lane index of the group's column 0 inside the tile
   int n, m, N;
-  RL_HD double* X(int col, int buf) const { return P->X + (tile * 2 * (N + 1) * n + (size_t)buf * (N + 1) * n) * RL_TILE + lane0 + col; }
-  RL_HD double* U(int col, int buf) const { return P->U + (tile * 2 * N * m + (size_t)buf * N * m) * RL_TILE + lane0 + col; }
-  RL_HD double* L(int col, int buf) const { return P->Lg + (tile * 2 * N * m * n + (size_t)buf * N * m * n) * RL_TILE + lane0 + col; }
-  RL_HD double* DL(int col, int buf) const { return P->DL + (tile * 2 * N * m + (size_t)buf * N * m) * RL_TILE + lane0 + col; }
+  RL_HD double* X(int col, int buf) const { return P->X + (tile * P->rec + (size_t)buf * (N + 1) * n) * RL_TILE + lane0 + col; }
+  RL_HD double* U(int col, int buf) const { return P->U + (tile * P->rec + (size_t)buf * N * m) * RL_TILE + lane0 + col; }
+  RL_HD double* L(int col, int buf) const { return P->Lg + (tile * P->rec + (size_t)buf * N * m * n) * RL_TILE + lane0 + col; }
+  RL_HD double* DL(int col, int buf) const { return P->DL + (tile * P->rec + (size_t)buf * N * m) * RL_TILE + lane0 + col; }
 };
 
 // backward pass over the trajectory (Xb, Ub), fused with approximate_model; is_opt: solve_approximate_dp! incl. the
