@@ -415,8 +415,11 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
     // Lane-level refill (persistent kernel pulling instances from a queue) is an opt-in experiment: measured
     // SLOWER than the static theta-sorted assignment (148 vs 120 ms on the bench fleet, profiles/r01_dynamic_refill_ab.jsonl)
     // because refilled lanes fall out of phase with their warp and most trips then carry a partially used optimising pass.
+    // (the device code is only there in a -DRL_ENABLE_DYNAMIC build; the host emulation keeps testing the logic)
+#if defined(RL_ENABLE_DYNAMIC)
     const char* e2 = getenv("RATILQR_DYNAMIC");
     ctx->dynamic = (e2 && e2[0] == '1');
+#endif
     if (ctx->dynamic) {
       CU(ctx->d_queue.reserve(8));
       P.queue = ctx->d_queue.as<unsigned int>();

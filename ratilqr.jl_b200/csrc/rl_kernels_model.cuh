@@ -21,8 +21,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_ileqg_solve(const __grid_cons
   Stage sg;
   sg.base = (UseStage<D>::value && P.use_stage) ? stage_area + threadIdx.x : nullptr;
   sg.stride = THREADS;
-  if (!WC && P.queue) solve_dynamic<D, CT>(P, b, sg);  // persistent: every thread keeps pulling instances
-  else if (b < (size_t)P.B) {
+#if defined(RL_ENABLE_DYNAMIC)  // opt-in build of a negative result (profiles/r01_dynamic_refill_ab.jsonl): persistent threads
+  if (!WC && P.queue) { solve_dynamic<D, CT>(P, b, sg); return; }  // that keep pulling instances from a queue
+#endif
+  if (b < (size_t)P.B) {
     if (sg.base) solve_instance<D, CT, WC, 1>(P, b, sg);
     else solve_instance<D, CT, WC, 0>(P, b, sg);
   }

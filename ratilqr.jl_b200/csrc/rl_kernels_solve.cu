@@ -11,7 +11,6 @@
 #include <cstring>
 #include <mutex>
 
-#include "rl_coop.cuh"
 #include "rl_kernels_model.cuh"
 #include "rl_host.hpp"
 #include "rl_launch.hpp"
@@ -68,7 +67,6 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
     switch (shape_override()) {
       // (the other shapes of the round-1 sweeps -- 64x{5,7,8}, 32x{8..20} -- lost everywhere and were removed: profiles/r01_tune_*.jsonl)
       case 0: launch_shape<D, CT, 64, 4>(P, st); return;    // 255 regs,  8 warps/SM
-      case 1: launch_shape<D, CT, 64, 6>(P, st); return;    // 168 regs, 12 warps/SM
       case 11: launch_shape<D, CT, 128, 3>(P, st); return;  // 168 regs, 128-thread CTAs
       default: {
         // Throughput shape (168 registers, 12 warps/SM) once the batch exceeds what it keeps resident at a time; below
@@ -78,12 +76,17 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
         static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
         // inv(W) from the constant bank instead of L1: measured 0.8 % SLOWER at full load (4.67 vs 4.71 M solves/s, same box,
         // two alternating runs each: profiles/r02_wconst_ab.txt) and equal in the latency regime, so it stays opt-in
+        // (those kernels are only compiled with -DRL_ENABLE_WCONST)
+#if defined(RL_ENABLE_WCONST)
         static const bool wc_on = [] { const char* e = getenv("RATILQR_WCONST"); return e && e[0] == '1'; }();
         const bool wc = wc_on && P.w_const && !P.queue;
-        if ((size_t)P.B <= (size_t)sms * 384 && !P.queue) {
-          if (wc) launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4, true>(P, st);
-          else launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4>(P, st);  // + constants pinned in L1
-        } else if (wc) launch_shape<D, CT, 128, 3, true>(P, st);
+        if (wc) {
+          if ((size_t)P.B <= (size_t)sms * 384) launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4, true>(P, st);
+          else launch_shape<D, CT, 128, 3, true>(P, st);
+          return;
+        }
+#endif
+        if ((size_t)P.B <= (size_t)sms * 384 && !P.queue) launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4>(P, st);  // + constants pinned in L1
         else launch_shape<D, CT, 128, 3>(P, st);   // best of the sweeps in profiles/r01_tune_*.jsonl
         return;
       }
@@ -91,81 +94,6 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
   } else {
     launch_shape<D, CT, 64, 4>(P, st);
   }
-}
-
-// ---- warp-cooperative variant: one warp (= one CTA) per instance, matrices + trajectories in shared memory -----
-template <class D, class CT>
-__global__ void __launch_bounds__(32) k_ileqg_solve_coop(const __grid_constant__ SolveParams P, double* traj_global) {
-  extern __shared__ double coop_smem[];
-  constexpr int n = D::n, m = D::m;
-  CoopWs<n, m>& w = *reinterpret_cast<CoopWs<n, m>*>(coop_smem);
-  const size_t inst = blockIdx.x;
-  const size_t td = coop_traj_doubles(n, m, P.N);
-  double* base = traj_global ? traj_global + inst * td : coop_smem + (sizeof(CoopWs<n, m>) + 7) / 8;
-  CoopTraj tj;
-  tj.X = base; tj.U = tj.X + (size_t)2 * (P.N + 1) * n; tj.Lg = tj.U + (size_t)2 * P.N * m; tj.DL = tj.Lg + (size_t)P.N * m * n;
-  int cur = 0;
-  const int lane = threadIdx.x;
-  if (coop_solve_instance<D, CT>(lane, P, inst, w, tj, cur)) coop_write_outputs<n, m>(lane, P, inst, tj, cur);
-}
-
-template <class D, class CT>
-size_t coop_smem_bytes(int N, bool traj_in_smem) {
-  size_t b = ((sizeof(CoopWs<D::n, D::m>) + 7) / 8) * 8;
-  if (traj_in_smem) b += coop_traj_doubles(D::n, D::m, N) * 8;
-  return b;
-}
-
-template <int MID, int CID>
-static int launch_coop_one(const SolveParams& P, double* traj_global, bool query_only, size_t* smem_out, cudaStream_t st) {
-  using D = Dyn<MID>;
-  using CT = Cost<CID, D::n, D::m>;
-  size_t smem = coop_smem_bytes<D, CT>(P.N, true);
-  bool in_smem = smem <= 200 * 1024;
-  if (in_smem && !query_only && traj_global) {
-    // Trajectories in shared memory minimise latency, but cap residency (5 warps/SM for the quadrotor).  When the batch
-    // exceeds one resident wave, keep only the per-stage matrices in shared memory and the trajectories in HBM
-    // (contiguous per instance, read once per stage): ~3x more resident warps to hide the shared-memory latency chains.
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t per_sm = (227 * 1024) / (smem + 1024);
-    const char* e = getenv("RATILQR_COOP_TRAJ");  // smem / global: force (tuning)
-    if (e ? (e[0] == 'g') : ((size_t)P.B > per_sm * (size_t)sms)) in_smem = false;
-  }
-  if (!in_smem) smem = coop_smem_bytes<D, CT>(P.N, false);
-  if (smem_out) *smem_out = smem;
-  if (query_only) return 0;
-  auto kfn = k_ileqg_solve_coop<D, CT>;
-  static size_t configured_dev[64] = {0};  // per device (function attributes do not carry over to another GPU)
-  int cur_dev = 0;
-  cudaGetDevice(&cur_dev);
-  size_t& configured = configured_dev[cur_dev & 63];
-  if (smem > configured) {
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    configured = smem;
-  }
-  kfn<<<P.B, 32, smem, st>>>(P, in_smem ? nullptr : traj_global);
-  return 0;
-}
-
-// coop kernels exist for every pair the serial kernel supports (the quadrotor also gets the diagonal-cost variant)
-#define RL_FOR_EACH_COOP_COMBO(X) RL_FOR_EACH_ILEQG_COMBO(X) RL_FOR_EACH_DIAG_COMBO(X) X(RATILQR_MODEL_QUADROTOR, RL_COST_QUAD_DIAG)
-
-int coop_smem_query(int model_id, int cost_id, int N, size_t* smem) {
-  SolveParams P; memset(&P, 0, sizeof(P)); P.N = N;
-#define X(MID, CID) if (model_id == MID && cost_id == CID) return launch_coop_one<MID, CID>(P, nullptr, true, smem, 0);
-  RL_FOR_EACH_COOP_COMBO(X)
-#undef X
-  return -1;
-}
-
-int launch_solve_coop(int model_id, int cost_id, const SolveParams& P, double* traj_global, cudaStream_t st) {
-#define X(MID, CID) if (model_id == MID && cost_id == CID) return launch_coop_one<MID, CID>(P, traj_global, false, nullptr, st);
-  RL_FOR_EACH_COOP_COMBO(X)
-#undef X
-  return -1;
 }
 
 int launch_solve(int model_id, int cost_id, const SolveParams& P, cudaStream_t st) {

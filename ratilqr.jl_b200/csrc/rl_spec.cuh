@@ -107,10 +107,23 @@ RL_HD int spec_backward(const SolveParams& P, const double* cp, double theta, bo
       }
       for (int i = 0; i < m; ++i) dl[i] = 0.0;
       if (!CT::stage(cp, k, x, u, true, q, qv, Q, r, R, Pm)) { fail = RATILQR_ST_DOMAIN; break; }
-      D::jac(P.mp, x, u, A, Bm);
+      // branch-free fast paths of rsqrt / sincos inside the stage, library routines on the recorded slow-path flag (as in
+      // rl::backward_pass; device only: the host emulation runs the plain routines)
+#if defined(__CUDA_ARCH__)
+      constexpr bool FRS = RL_DEFER_PD && RL_FAST_RSQRT;
+#else
+      constexpr bool FRS = false;
+#endif
+      bool lin_slow = false;
+      if (FRS) jac_nb<D>(P.mp, x, u, A, Bm, lin_slow); else D::jac(P.mp, x, u, A, Bm);
       const size_t wo = P.W_tv ? (size_t)k * n * n : 0;
-      int rc = riccati_stage<Tr, false, true, true>(theta, mu, P.W + wo, P.Winv + wo, P.detW[P.W_tv ? k : 0], S, sv, s, q, qv, Q, r,
-                                                    R, Pm, A, Bm, L, dl, RL_FUSED ? &detprod : nullptr, is_opt);
+      int rc = riccati_stage<Tr, false, true, true, FRS>(theta, mu, P.W + wo, P.Winv + wo, P.detW[P.W_tv ? k : 0], S, sv, s, q, qv, Q, r,
+                                                         R, Pm, A, Bm, L, dl, RL_FUSED ? &detprod : nullptr, is_opt, lin_slow);
+      if (FRS && rc == 3) {
+        if (lin_slow) D::jac(P.mp, x, u, A, Bm);
+        rc = riccati_stage<Tr, false, true, true>(theta, mu, P.W + wo, P.Winv + wo, P.detW[P.W_tv ? k : 0], S, sv, s, q, qv, Q, r,
+                                                  R, Pm, A, Bm, L, dl, RL_FUSED ? &detprod : nullptr, is_opt);
+      }
       if (rc == 1) { fail = is_opt ? RATILQR_ST_M_NOT_PD_OPT : RATILQR_ST_M_NOT_PD_INIT; break; }
       if (RL_FUSED && !(detprod > 1e-250 && detprod < 1e250)) { logacc += log(detprod); detprod = 1.0; }
       if (rc == 2) {  // optimising lanes only: increase_mu_and_delta! and restart the sweep (:372-378)
@@ -198,7 +211,13 @@ RL_HD int spec_rollout(const SolveParams& P, const double* Xc, const double* Uc,
     }
     if (acc != acc) has_nan = true;
     if (acc > best) best = acc;
-    if (!D::f(P.mp, x, u, xn)) { if (staged) rl_stage_wait(); return RATILQR_ST_DOMAIN; }
+    bool f_ok;
+#if defined(__CUDA_ARCH__)
+    if (RL_FAST_RSQRT) { bool f_slow = false; f_ok = f_nb<D>(P.mp, x, u, xn, f_slow); if (f_slow) f_ok = D::f(P.mp, x, u, xn); }
+    else
+#endif
+      f_ok = D::f(P.mp, x, u, xn);
+    if (!f_ok) { if (staged) rl_stage_wait(); return RATILQR_ST_DOMAIN; }
     st_vec<m>(Un + (size_t)k * m * B, B, u);
     st_vec<n>(Xn + (size_t)(k + 1) * n * B, B, xn);
     for (int i = 0; i < n; ++i) x[i] = xn[i];

@@ -11,7 +11,7 @@ import json,sys
 v=sys.argv[1]
 d=json.loads(open("gpurun_out/ab_tmp.log").read().strip().splitlines()[-1])
 lat=d.get("latency",{})
-print(v, round(d["value"]), round(d["ms_per_step"],2), "frac", round(d["roofline"]["frac"],4), "mhz", d["clocks"]["sm_mhz"], "c2_single", round(d["c2_single"]["ms_per_batch"],3), "e2e", round(d["e2e"]["value"]), "mpc_fleet", round(d["mpc_step"]["ms_per_fleet_step"],1), "lat", json.dumps(lat)[:300])
+print(v, round(d["value"]), round(d["ms_per_step"],2), "frac", round(d["roofline"]["frac"],4), "mhz", d["clocks"]["sm_mhz"], "c2_single", round(d["c2_single"]["ms_per_batch"],3), "e2e", round(d["e2e"]["value"]), "mpc_fleet", round(d["mpc_step"]["ms_per_fleet_step"],1), "lat(c2_1x1024, mpc_single, c3_nm ms)", [round(lat[k]["gpu_ms"],2) for k in ("c2_single_1x1024","mpc_step_single_problem","c3_rat_ilqr_pp_quadrotor") if k in lat])
 PY
 done
 done

@@ -14,5 +14,5 @@ NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=
 $NV $flags -c $src/rl_kernels_solve.cu -o $out/solve_$name.o &
 $NV $flags -c $src/rl_kernels_spec.cu -o $out/spec_$name.o &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/lib_$name.so $out/solve_$name.o $out/spec_$name.o $src/rl_kernels_comp.o $src/rl_capi.o $src/rl_user_host.o -ldl
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/lib_$name.so $out/solve_$name.o $out/spec_$name.o $src/rl_kernels_coop.o $src/rl_kernels_comp.o $src/rl_capi.o $src/rl_user_host.o -ldl
 echo built $out/lib_$name.so
