@@ -323,7 +323,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   const size_t cols = ctx->spec_G ? B * ctx->spec_G : B;  // workspace columns: one per thread
   const size_t pol = ctx->spec_G ? 2 : 1;                 // the speculative kernel double-buffers the policy (Lg, DL)
   const size_t Bp = (cols + 31) / 32 * 32;  // the workspace is tiled in groups of 32 thread slots
-  const rl::WsLayout wl = rl::ws_layout(n, m, N, (int)pol);  // one allocation of per-tile records (rl::SolveParams::X)
+  const rl::WsLayout wl = rl::ws_layout(n, m, N, (int)pol, rl::model_naux(desc->model_id));  // one allocation of per-tile records (rl::SolveParams::X)
   CU(ctx->d_X.reserve(wl.rec * Bp * 8));
   CU(ctx->d_value.reserve(B * 8));
   CU(ctx->d_mu.reserve(B * 8));
@@ -356,7 +356,7 @@ static int stage_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* desc, co
   P.theta = ctx->d_theta.as<double>();
   P.mu_min = opts->mu_min; P.delta_0 = opts->delta_0; P.lambda = opts->lambda; P.d = opts->d;
   P.iter_max = opts->iter_max; P.eps_auto = opts->adaptive_eps_init; P.eps_init = opts->eps_init; P.eps_min = opts->eps_min;
-  P.X = ctx->d_X.as<double>(); P.U = P.X + wl.oU * 32; P.Lg = P.X + wl.oLg * 32; P.DL = P.X + wl.oDL * 32; P.rec = wl.rec;
+  P.X = ctx->d_X.as<double>(); P.U = P.X + wl.oU * 32; P.Lg = P.X + wl.oLg * 32; P.DL = P.X + wl.oDL * 32; P.AUX = P.X + wl.oAux * 32; P.rec = wl.rec;
   P.value = ctx->d_value.as<double>(); P.status = ctx->d_status.as<int32_t>(); P.iters = ctx->d_iters.as<int32_t>();
   P.trials = ctx->d_trials.as<int32_t>(); P.restarts = ctx->d_restarts.as<int32_t>();
   P.mu_out = ctx->d_mu.as<double>(); P.d_out = ctx->d_d.as<double>(); P.cur = ctx->d_cur.as<int32_t>();

@@ -1,2 +1,2 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-scripts/ab_variants.sh gpurun_out/r02_ab_specfrs.txt 2 build/variants/lib_head.so ratilqr.jl_b200/csrc/libratilqr_b200.so
+python bench.py > gpurun_out/r02_bench_v12.json 2> gpurun_out/r02_bench_v12.err; tail -c 600 gpurun_out/r02_bench_v12.json

@@ -155,7 +155,7 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
   const bool spec = g_spec && !g_coop && !g_dynamic && n <= 6 && desc->model_id < 1000 && desc->cost_id < 100;
   const size_t cols = spec ? B * g_spec : B, pol = spec ? 2 : 1;
   const size_t Bp = (cols + 31) / 32 * 32;  // warp-tiled workspace
-  const WsLayout wl = ws_layout(n, m, N, (int)pol);  // per-tile records, as the device library lays them out
+  const WsLayout wl = ws_layout(n, m, N, (int)pol, model_naux(desc->model_id));  // per-tile records, as the device library lays them out
   std::vector<double> ws(wl.rec * Bp, 0.0), value(B), mu(B), dcur(B), eps;
   double *X = ws.data(), *U = X + wl.oU * 32, *Lg = X + wl.oLg * 32;
   std::vector<int32_t> status(B), iters(B), trials(B), restarts(B), cur(B);
@@ -170,7 +170,7 @@ int32_t hostemu_ileqg_solve_batch(void*, const ratilqr_problem_desc* desc, const
   P.x0 = in->x0; P.x0_count = in->x0_count; P.u_init = in->u_init; P.u_count = in->u_count; P.theta = in->theta;
   P.mu_min = opts->mu_min; P.delta_0 = opts->delta_0; P.lambda = opts->lambda; P.d = opts->d;
   P.iter_max = opts->iter_max; P.eps_auto = opts->adaptive_eps_init; P.eps_init = opts->eps_init; P.eps_min = opts->eps_min;
-  P.X = X; P.U = U; P.Lg = Lg; P.DL = X + wl.oDL * 32; P.rec = wl.rec;
+  P.X = X; P.U = U; P.Lg = Lg; P.DL = X + wl.oDL * 32; P.AUX = X + wl.oAux * 32; P.rec = wl.rec;
   P.value = value.data(); P.status = status.data(); P.iters = iters.data(); P.trials = trials.data();
   P.restarts = restarts.data(); P.mu_out = mu.data(); P.d_out = dcur.data(); P.cur = cur.data();
   P.eps_hist = cap ? eps.data() : nullptr; P.eps_hist_cap = cap;
