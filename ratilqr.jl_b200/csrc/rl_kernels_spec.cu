@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(32) k_ileqg_solve_spec(const __grid_constant__
     const bool work = alive && !S.done;
     SpecLaneRes r;
     r.st_roll = 0; r.rc = 0; r.nw = 0.0; r.dmax = 0.0; r.mu = 0.0; r.delta = 0.0; r.restarts = 0;
-    if (work) r = spec_lane_work<D, CT>(P, C, g, S, cp, theta, p, sg);
+    if (work) r = sg.base ? spec_lane_work<D, CT, 1>(P, C, g, S, cp, theta, p, sg) : spec_lane_work<D, CT, 0>(P, C, g, S, cp, theta, p, sg);
     __syncwarp(full);  // candidates / speculative policies written above are read by the other lanes of the group below
     SpecLaneRes res[G];
 #pragma unroll

@@ -59,7 +59,8 @@ struct SpecCols {
 // backward pass over the trajectory (Xb, Ub), fused with approximate_model; is_opt: solve_approximate_dp! incl. the
 // mu-restart loop (ileqg.jl:341-406), gains / dl written to (Ldst, DLdst); else solve_approximate_dp (:412-465) of the
 // policy Lsrc (zeroL: L = 0) with dl = zeros(m) (:447-451).  Same staging scheme as rl::backward_pass.
-template <class D, class CT>
+// SM: staging decided at run time by sg.base (-1: host emulation) or at compile time (0 / 1: the kernel dispatches once)
+template <class D, class CT, int SM = -1>
 RL_HD int spec_backward(const SolveParams& P, const double* cp, double theta, bool is_opt, bool zeroL, const double* Xb,
                         const double* Ub, const double* Lsrc, double* Ldst, double* DLdst, double& mu, double& delta,
                         int& restarts, double& value, Stage sg) {
@@ -67,7 +68,7 @@ RL_HD int spec_backward(const SolveParams& P, const double* cp, double theta, bo
   using Tr = StageTraits<D, CT>;
   constexpr size_t B = RL_TILE;
   const int N = P.N;
-  const bool staged = UseStage<D>::value && sg.base != nullptr;
+  const bool staged = UseStage<D>::value && (SM < 0 ? sg.base != nullptr : SM == 1);
   const bool needL = !is_opt && !zeroL;
   auto fetch = [&](int k) {
     double* s0 = sg.base + (size_t)(k & 1) * RL_STAGE_NV * sg.stride;
@@ -151,13 +152,13 @@ RL_HD int spec_backward(const SolveParams& P, const double* cp, double theta, bo
 
 // closed-loop rollout around (Xc, Uc) with l + eps*dl and gains L of the policy (Lp, DLp) into (Xn, Un)
 // (ileqg.jl:509, :62-87); init: open-loop rollout of the initial controls (:225-228).  Mirrors rl::rollout_candidate.
-template <class D>
+template <class D, int SM = -1>
 RL_HD int spec_rollout(const SolveParams& P, const double* Xc, const double* Uc, const double* Lp, const double* DLp,
                        double* Xn, double* Un, double eps, bool init, double& dmax, Stage sg) {
   constexpr int n = D::n, m = D::m;
   constexpr size_t B = RL_TILE;
   const int N = P.N;
-  const bool staged = UseStage<D>::value && sg.base != nullptr;
+  const bool staged = UseStage<D>::value && (SM < 0 ? sg.base != nullptr : SM == 1);
   auto fetch = [&](int k) {
     double* s0 = sg.base + (size_t)(k & 1) * RL_STAGE_NV * sg.stride;
     for (int i = 0; i < n; ++i) rl_stage_put(s0 + (size_t)i * sg.stride, Xc + ((size_t)k * n + i) * B);
@@ -240,7 +241,7 @@ RL_HD int spec_free_traj_buf(const SpecState& S, int g) { return (g == S.cur_col
 RL_HD int spec_free_pol_buf(const SpecState& S, int g) { return (S.has_pol && g == S.pol_col) ? (S.pol_buf ^ 1) : 0; }
 
 // one round of lane g of the group: rollout of candidate j = g/2, then its evaluating (g even) / optimising (g odd) pass
-template <class D, class CT>
+template <class D, class CT, int SM = -1>
 RL_HD SpecLaneRes spec_lane_work(const SolveParams& P, const SpecCols& C, int g, const SpecState& S, const double* cp,
                                  double theta, size_t p, Stage sg) {
   constexpr int n = D::n, m = D::m;
@@ -258,17 +259,17 @@ RL_HD SpecLaneRes spec_lane_work(const SolveParams& P, const SpecCols& C, int g,
     for (int i = 0; i < n; ++i) Xc[(size_t)i * RL_TILE] = x0[i];
     for (int k = 0; k < N; ++k)
       for (int j = 0; j < m; ++j) Uc[((size_t)k * m + j) * RL_TILE] = ui[(size_t)k * m + j];
-    r.st_roll = spec_rollout<D>(P, Xc, Uc, C.L(g, 0), C.DL(g, 0), C.X(g, 0), C.U(g, 0), 0.0, true, dmax, sg);
+    r.st_roll = spec_rollout<D, SM>(P, Xc, Uc, C.L(g, 0), C.DL(g, 0), C.X(g, 0), C.U(g, 0), 0.0, true, dmax, sg);
   } else {
     double eps = S.eps;
     for (int i = 0; i < (g >> 1); ++i) eps *= P.lambda;  // the eps the serial loop would reach at its (g/2)-th further trial
-    r.st_roll = spec_rollout<D>(P, C.X(S.cur_col, S.cur_buf), C.U(S.cur_col, S.cur_buf), C.L(S.pol_col, S.pol_buf),
+    r.st_roll = spec_rollout<D, SM>(P, C.X(S.cur_col, S.cur_buf), C.U(S.cur_col, S.cur_buf), C.L(S.pol_col, S.pol_buf),
                                 C.DL(S.pol_col, S.pol_buf), C.X(g, fb), C.U(g, fb), eps, false, dmax, sg);
   }
   r.dmax = dmax;
   if (r.st_roll) return r;
   double val = rl_inf();
-  r.rc = spec_backward<D, CT>(P, cp, theta, is_opt, S.init, C.X(g, fb), C.U(g, fb), C.L(S.pol_col, S.pol_buf), C.L(g, pb),
+  r.rc = spec_backward<D, CT, SM>(P, cp, theta, is_opt, S.init, C.X(g, fb), C.U(g, fb), C.L(S.pol_col, S.pol_buf), C.L(g, pb),
                               C.DL(g, pb), r.mu, r.delta, r.restarts, val, sg);
   r.nw = val;
   return r;
