@@ -216,8 +216,10 @@ RL_HD void philox_normal2(uint64_t seed, uint64_t stream, uint32_t step, uint32_
   double u2 = ((double)(((uint64_t)o[2] << 21) ^ (uint64_t)(o[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
   double rad = sqrt(-2.0 * log(u1));
   double ang = 6.283185307179586476925286766559 * u2;
-  *z0 = rad * cos(ang);
-  *z1 = rad * sin(ang);
+  double sn, cs;
+  rl_sincos_any(ang, &sn, &cs);  // one range reduction for the pair (same bits as cos(ang), sin(ang))
+  *z0 = rad * cs;
+  *z1 = rad * sn;
 }
 RL_HD double philox_uniform(uint64_t seed, uint64_t stream, uint32_t step, uint32_t lane, int which) {
   uint32_t o[4];

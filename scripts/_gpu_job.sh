@@ -1,2 +1,7 @@
-python scripts/check_multi_gpu.py 2 > gpurun_out/r02_v12_multi_gpu_2dev.jsonl 2> gpurun_out/r02_v12_multi_gpu_2dev.err; tail -n 8 gpurun_out/r02_v12_multi_gpu_2dev.jsonl | cut -c1-260; tail -2 gpurun_out/r02_v12_multi_gpu_2dev.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 8 --warmup 3 --no-cpu-baseline --no-latency-cases > gpurun_out/r02_v12_scale_2gpu.json 2> gpurun_out/r02_v12_scale_2gpu.err; tail -c 1500 gpurun_out/r02_v12_scale_2gpu.json | head -c 1500; tail -2 gpurun_out/r02_v12_scale_2gpu.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_sincos_any.json 2> gpurun_out/bench_sincos_any.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_sincos_any.json').read().strip().splitlines()[-1])
+print("value", d["value"], "c4 ms", d["roofline_c4"]["ms_per_solve"], d["roofline_c4"]["rollouts_per_sec"], "c3", d["roofline_c3"]["ms_per_launch"], d["roofline_c3"]["solves_per_sec"], "mc_eval", d["mpc_step"].get("mc_eval"), "lat", [d["latency"][k]["gpu_ms"] for k in d["latency"] if k!="cpu_threads"])
+PY
