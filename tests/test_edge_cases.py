@@ -88,3 +88,25 @@ def test_unregistered_closures_are_rejected():
                                                              lambda k: np.eye(2), 3)
     with pytest.raises(TypeError):
         prob.spec()  # arbitrary closures are not accelerated and there is no CPU fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec_mode", ["0", "8"])
+def test_heading_beyond_the_fast_path_of_sincos(gpu_be, oracle_be, spec_mode):
+    """|psi| >= 2^31: the branch-free sincos of the solve kernels (rl_sincos_nb) only RECORDS that the library routine's
+    Payne-Hanek slow path is needed; the stage (backward passes) / the step (rollout) is then redone through the library
+    routine.  Thread-per-instance kernel (RATILQR_SPEC=0) and speculative latency kernel against the oracle."""
+    import os
+    N = 20
+    cost = wl.unicycle_cost(goal=(5.0, 5.0, 3.0e9, 0.0))
+    W = np.diag([1e-2, 1e-2, 1e-3, 1e-2]) * 0.1
+    prob = R.FiniteHorizonRiskSensitiveOptimalControlProblem(R.Unicycle(0.1), cost.c, cost.h, R.ConstantCovariance(W), N)
+    x0 = np.array([0.0, 0.0, 3.0e9 + 0.3, 1.0])
+    os.environ["RATILQR_SPEC"] = spec_mode
+    try:
+        be = R.new_backend(0)
+        g, o = check_solve(be, oracle_be, prob.spec(), x0, np.zeros((2, N)), [0.0, 0.3, 1.0, 2.5], opts=R.make_opts(iter_max=15))
+        be.close()
+    finally:
+        del os.environ["RATILQR_SPEC"]
+    assert np.all(o["status"] == 0) and np.all(o["iters"] >= 3)
