@@ -30,6 +30,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_ileqg_solve(const __grid_cons
   }
 }
 
+// the same kernel under an explicit register cap (__maxnreg__): launch bounds only offer the caps 65536 / (THREADS * MINB)
+// rounded down by ptxas to 128 / 168 / 255 here; tuning shapes of rl_kernels_solve.cu (RL_TUNE_SHAPES)
+#if defined(RL_TUNE_SHAPES)
+template <class D, class CT, int THREADS, int MAXREG>
+__global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) k_ileqg_solve_r(const __grid_constant__ SolveParams P) {
+  extern __shared__ double stage_area[];
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Stage sg;
+  sg.base = stage_area + threadIdx.x;
+  sg.stride = THREADS;
+  if (b < (size_t)P.B) solve_instance<D, CT, false, 1>(P, b, sg);
+}
+#endif
+
 // ---- rollouts / cost / linearize: thread = instance (host layout, instance slowest) ----------
 template <class D>
 __global__ void k_rollout_open(CompArgs a) {

@@ -52,6 +52,26 @@ static void launch_shape(const SolveParams& P, cudaStream_t st) {
   k_ileqg_solve<D, CT, THREADS, MINB, WC><<<blocks, THREADS, smem, st>>>(P);
 }
 
+#if defined(RL_TUNE_SHAPES)
+template <class D, class CT, int THREADS, int MAXREG>
+static void launch_shape_r(const SolveParams& P, cudaStream_t st) {
+  const int blocks = (P.B + THREADS - 1) / THREADS;
+  const size_t smem = (size_t)2 * RL_STAGE_NV * THREADS * sizeof(double);
+  constexpr int resident = 65536 / (MAXREG * THREADS);
+  auto kfn = k_ileqg_solve_r<D, CT, THREADS, MAXREG>;
+  static bool configured = false;
+  if (!configured) {
+    configured = true;
+    int pct = (int)((resident * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 5;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, THREADS, smem);
+    if (getenv("RATILQR_DEBUG")) fprintf(stderr, "[ratilqr] k_ileqg_solve_r threads=%d maxreg=%d smem=%zu -> %d resident CTAs/SM\n", THREADS, MAXREG, smem, nb);
+  }
+  kfn<<<blocks, THREADS, smem, st>>>(P);
+}
+#endif
+
 // launch shape = (threads per CTA, min resident CTAs per SM => register cap).  The default was chosen from
 // the sweep recorded in profiles/; RATILQR_SOLVE_SHAPE=<idx> overrides it for tuning runs.
 static int shape_override() {
@@ -68,6 +88,12 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
       // (the other shapes of the round-1 sweeps -- 64x{5,7,8}, 32x{8..20} -- lost everywhere and were removed: profiles/r01_tune_*.jsonl)
       case 0: launch_shape<D, CT, 64, 4>(P, st); return;    // 255 regs,  8 warps/SM
       case 11: launch_shape<D, CT, 128, 3>(P, st); return;  // 168 regs, 128-thread CTAs
+#if defined(RL_TUNE_SHAPES)
+      case 20: launch_shape_r<D, CT, 64, 144>(P, st); return;   // 14 warps/SM
+      case 21: launch_shape_r<D, CT, 32, 152>(P, st); return;   // 13 warps/SM
+      case 22: launch_shape_r<D, CT, 96, 136>(P, st); return;   // 15 warps/SM
+      case 23: launch_shape_r<D, CT, 64, 160>(P, st); return;   // 12 warps/SM, 64-thread CTAs
+#endif
       default: {
         // Throughput shape (168 registers, 12 warps/SM) once the batch exceeds what it keeps resident at a time; below
         // that every instance is resident anyway and the 255-register build wins on latency (fewer spills, more ILP per
