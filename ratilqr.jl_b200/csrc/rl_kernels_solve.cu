@@ -93,6 +93,8 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
       case 21: launch_shape_r<D, CT, 32, 152>(P, st); return;   // 13 warps/SM
       case 22: launch_shape_r<D, CT, 96, 136>(P, st); return;   // 15 warps/SM
       case 23: launch_shape_r<D, CT, 64, 160>(P, st); return;   // 12 warps/SM, 64-thread CTAs
+      case 24: launch_shape<D, CT, 128, 4>(P, st); return;      // 128 regs, 16 warps/SM
+      case 25: launch_shape<D, CT, 64, 8>(P, st); return;       // 128 regs, 16 warps/SM, 64-thread CTAs
 #endif
       default: {
         // Throughput shape (168 registers, 12 warps/SM) once the batch exceeds what it keeps resident at a time; below
