@@ -200,27 +200,35 @@ __device__ __forceinline__ bool key_less(double ca, int ia, double cb, int ib) {
   return ia < ib;
 }
 
+// rank by counting on the total order (cost, index) = the position a stable sort would give; one WARP per candidate, lanes
+// stride over the other candidates (integer counts: exact whatever the reduction shape)
 __global__ void __launch_bounds__(256) k_pets_rank(int C, int num_elite, const double* cost, int32_t* elite_idx) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= C) return;
-  double ci = cost[i];
+  const double ci = cost[i];
   int rank = 0;
-  for (int j = 0; j < C; ++j) rank += key_less(cost[j], j, ci, i) ? 1 : 0;
-  if (rank < num_elite) elite_idx[rank] = i;
+  for (int j = lane; j < C; j += 32) rank += key_less(cost[j], j, ci, i) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+  if (lane == 0 && rank < num_elite) elite_idx[rank] = i;
 }
 
-// compute_new_distribution (pets.jl:173-191): thread = (tt, j); sums run over the elites in sorted order
-__global__ void k_pets_refit(int m, int N, int num_elite, double smoothing, const double* controls,
-                             const int32_t* elite_idx, double* mu, double* Sigma) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+// compute_new_distribution (pets.jl:173-191): one warp per (tt, j).  The lanes gather the elites' controls into shared
+// memory; lane 0 then sums them in sorted order (the same sequence of additions as a serial loop over the elites)
+__global__ void __launch_bounds__(32) k_pets_refit(int m, int N, int num_elite, double smoothing, const double* controls,
+                                                   const int32_t* elite_idx, double* mu, double* Sigma) {
+  extern __shared__ double elite_vals[];
+  const int t = blockIdx.x, lane = threadIdx.x;
   if (t >= N * m) return;
-  int tt = t / m, j = t % m;
+  const int tt = t / m, j = t % m;
+  for (int e = lane; e < num_elite; e += 32) elite_vals[e] = controls[(size_t)elite_idx[e] * m * N + (size_t)tt * m + j];
+  __syncwarp();
+  if (lane != 0) return;
   double sum = 0.0;
-  for (int e = 0; e < num_elite; ++e) sum += controls[(size_t)elite_idx[e] * m * N + (size_t)tt * m + j];
+  for (int e = 0; e < num_elite; ++e) sum += elite_vals[e];
   double mean = sum / num_elite;
   double ss = 0.0;
   for (int e = 0; e < num_elite; ++e) {
-    double d = controls[(size_t)elite_idx[e] * m * N + (size_t)tt * m + j] - mean;
+    double d = elite_vals[e] - mean;
     ss += d * d;
   }
   double var = ss / (num_elite - 1);  // Julia var(): unbiased
@@ -235,8 +243,10 @@ __global__ void k_pets_refit(int m, int N, int num_elite, double smoothing, cons
 void launch_pets_refit(int m, int N, int C, int num_elite, double smoothing, const double* controls,
                        const double* cost, double* mu, double* Sigma, int32_t* elite_idx, int32_t*,
                        cudaStream_t st) {
-  k_pets_rank<<<RL_BLOCKS(C, 256), 256, 0, st>>>(C, num_elite, cost, elite_idx);
-  k_pets_refit<<<RL_BLOCKS(N * m, 64), 64, 0, st>>>(m, N, num_elite, smoothing, controls, elite_idx, mu, Sigma);
+  k_pets_rank<<<(unsigned)(((size_t)C * 32 + 255) / 256), 256, 0, st>>>(C, num_elite, cost, elite_idx);
+  const size_t smem = (size_t)num_elite * sizeof(double);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_pets_refit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_pets_refit<<<N * m, 32, smem, st>>>(m, N, num_elite, smoothing, controls, elite_idx, mu, Sigma);
 }
 
 
