@@ -1031,8 +1031,10 @@ static int mc_rollout_internal(ratilqr_ctx* ctx, const ratilqr_problem_desc* des
   if (int rc = check_launch(ctx, "k_mc_rollout", um ? 0 : 1)) return rc;
   if (stats) {
     CU(ctx->s[7].reserve((size_t)P * 24));
-    rll::launch_mc_stats(a.J, n_samples, P, theta_risk, ctx->s[7].as<double>(), ctx->stream);
-    if (int rc = check_launch(ctx, "k_mc_stats")) return rc;
+    const size_t scr = rll::mc_stats_scratch_doubles(n_samples, P);  // > 0: chunked reductions (many samples per problem)
+    if (scr) CU(ctx->s[8].reserve(scr * 8));
+    rll::launch_mc_stats(a.J, n_samples, P, theta_risk, ctx->s[7].as<double>(), scr ? ctx->s[8].as<double>() : nullptr, ctx->stream);
+    if (int rc = check_launch(ctx, "k_mc_stats", scr ? (theta_risk > 0.0 ? 5 : 3) : 1)) return rc;
     DOWNSYNC(stats, ctx->s[7].p, (size_t)P * 24);
   }
   DOWNSYNC(J, a.J, S * 8);

@@ -139,8 +139,54 @@ __global__ void __launch_bounds__(256) k_mc_stats(const double* J, int n_samples
   if (threadIdx.x == 0) { stats[3 * p] = mean; stats[3 * p + 1] = var; stats[3 * p + 2] = risk; }
 }
 
-void launch_mc_stats(const double* J, int n_samples, int P, double theta_risk, double* stats, cudaStream_t st) {
-  k_mc_stats<<<P, 256, 0, st>>>(J, n_samples, theta_risk, stats);
+// Large sample counts (one problem x 2^20 samples took 2 ms in the single CTA above): the same four reductions in chunks of
+// RL_MC_CHUNK samples, one CTA per (chunk, problem); every CTA first combines the previous stage's per-chunk partials in
+// chunk order (<= a few hundred values), so the result is a fixed function of (n_samples, data): deterministic, independent
+// of the launch.  mode 0: sum x | 1: sum (x - mean)^2 | 2: max theta x | 3: sum exp(theta x - max) | 4: final combine.
+constexpr int RL_MC_CHUNK = 8192;
+__global__ void __launch_bounds__(256) k_mc_stats_chunked(const double* J, int n_samples, int n_chunks, double theta_risk, int mode,
+                                                          double* part /* [P][4][n_chunks] */, double* stats) {
+  __shared__ double sh[33];
+  const int p = blockIdx.y, c = blockIdx.x;
+  const double* Jp = J + (size_t)p * n_samples;
+  double* pp = part + (size_t)p * 4 * n_chunks;
+  auto combine = [&](int which, bool is_max) {  // every thread: the partials of stage `which` in chunk order
+    double a = is_max ? -HUGE_VAL : 0.0;
+    for (int k = 0; k < n_chunks; ++k) a = is_max ? fmax(a, pp[which * n_chunks + k]) : a + pp[which * n_chunks + k];
+    return a;
+  };
+  const int lo = c * RL_MC_CHUNK, hi = min(n_samples, lo + RL_MC_CHUNK);
+  if (mode == 4) {
+    if (threadIdx.x != 0 || c != 0) return;
+    const double mean = combine(0, false) / n_samples;
+    const double ss = combine(1, false);
+    double risk = mean;
+    if (theta_risk > 0.0) { const double mx = combine(2, true); risk = (mx + log(combine(3, false) / n_samples)) / theta_risk; }
+    stats[3 * p] = mean; stats[3 * p + 1] = n_samples > 1 ? ss / (n_samples - 1) : 0.0; stats[3 * p + 2] = risk;
+    return;
+  }
+  double acc = (mode == 2) ? -HUGE_VAL : 0.0;
+  if (mode == 0) { for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += Jp[i]; }
+  else if (mode == 1) { const double mean = combine(0, false) / n_samples; for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) { double d = Jp[i] - mean; acc += d * d; } }
+  else if (mode == 2) { for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc = fmax(acc, theta_risk * Jp[i]); }
+  else { const double mx = combine(2, true); for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += exp(theta_risk * Jp[i] - mx); }
+  const double r = (mode == 2) ? block_reduce(acc, OpMax(), -HUGE_VAL, sh) : block_reduce(acc, OpAdd(), 0.0, sh);
+  if (threadIdx.x == 0) pp[mode * n_chunks + c] = r;
+}
+
+void launch_mc_stats(const double* J, int n_samples, int P, double theta_risk, double* stats, double* scratch, cudaStream_t st) {
+  const int n_chunks = (n_samples + RL_MC_CHUNK - 1) / RL_MC_CHUNK;
+  if (n_chunks < 4 || !scratch) { k_mc_stats<<<P, 256, 0, st>>>(J, n_samples, theta_risk, stats); return; }
+  const dim3 grid(n_chunks, P);
+  for (int mode = 0; mode < 4; ++mode) {
+    if (mode >= 2 && !(theta_risk > 0.0)) continue;
+    k_mc_stats_chunked<<<grid, 256, 0, st>>>(J, n_samples, n_chunks, theta_risk, mode, scratch, stats);
+  }
+  k_mc_stats_chunked<<<dim3(1, P), 32, 0, st>>>(J, n_samples, n_chunks, theta_risk, 4, scratch, stats);
+}
+size_t mc_stats_scratch_doubles(int n_samples, int P) {
+  const int n_chunks = (n_samples + RL_MC_CHUNK - 1) / RL_MC_CHUNK;
+  return n_chunks < 4 ? 0 : (size_t)P * 4 * n_chunks;
 }
 
 int launch_pets_costs(const PetsArgs& a, cudaStream_t st) {

@@ -57,7 +57,9 @@ int launch_riccati(const RiccatiArgs& a, cudaStream_t st);
 
 int launch_mc_rollout(const McArgs& a, cudaStream_t st);
 // per-problem mean / unbiased variance / entropic risk of J (deterministic single-block reduction)
-void launch_mc_stats(const double* J, int n_samples, int P, double theta_risk, double* stats, cudaStream_t st);
+// scratch: mc_stats_scratch_doubles(n_samples, P) doubles (0 = the one-CTA-per-problem kernel is used)
+void launch_mc_stats(const double* J, int n_samples, int P, double theta_risk, double* stats, double* scratch, cudaStream_t st);
+size_t mc_stats_scratch_doubles(int n_samples, int P);
 
 int launch_pets_costs(const PetsArgs& a, cudaStream_t st);
 // u = mu_t + chol_lower(Sigma_t) z ; z injected (m*N*C) or Philox. returns via err[0] != 0 if a Sigma_t is not PD

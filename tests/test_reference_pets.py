@@ -138,3 +138,27 @@ def test_mc_rollout_philox_statistical(gpu_be, oracle_be):
     assert g["stats"][0, 2] >= g["stats"][0, 0]  # entropic risk >= mean (Jensen)
     g2 = gpu_be.mc_rollout(spec, xbar, l, L, 8192, seed=5, theta_risk=1.0)
     assert np.array_equal(g["J"], g2["J"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("theta_risk", [0.0, 0.5])
+def test_mc_stats_of_many_samples_per_problem(gpu_be, theta_risk):
+    """>= 4 chunks of 8,192 samples per problem go through the chunked reductions (k_mc_stats_chunked): mean, unbiased
+    variance and the entropic risk (1/theta) log E exp(theta J) against numpy on the returned costs"""
+    prob, x0, u = wl.c2_problem(N=12)
+    spec = prob.spec()
+    r = gpu_be.ileqg_solve_batch(spec, x0, u, [0.5])
+    xbar, l, L = r["x"][..., 0], r["l"][..., 0], r["L"][..., 0]
+    P, S = 2, 40000
+    n0 = gpu_be.launch_count()
+    g = gpu_be.mc_rollout(spec, np.stack([xbar, xbar], -1), np.stack([l, l], -1), np.stack([L, L], -1), S, seed=11,
+                          theta_risk=theta_risk, P=P)
+    assert gpu_be.launch_count() - n0 == 1 + (5 if theta_risk > 0 else 3)
+    J = g["J"].reshape(P, S)
+    assert np.all(np.isfinite(J)) and not np.array_equal(J[0], J[1])
+    for p in range(P):
+        mean, var, risk = g["stats"][p]
+        assert abs(mean - J[p].mean()) < 1e-12 * abs(J[p].mean())
+        assert abs(var - J[p].var(ddof=1)) < 1e-10 * J[p].var(ddof=1)
+        ref = J[p].mean() if theta_risk == 0 else (np.log(np.mean(np.exp(theta_risk * J[p] - (theta_risk * J[p]).max()))) + (theta_risk * J[p]).max()) / theta_risk
+        assert abs(risk - ref) < 1e-12 * abs(ref)
