@@ -149,6 +149,56 @@ template <class Tr, bool OPT, bool HAS_DL>
 RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, double mu, const double* RL_RESTRICT Winv,
                                    double detW, double& s, double* detprod) {
   constexpr int n = Tr::n, m = Tr::m;
+  double detM = 1.0;
+#if defined(__CUDA_ARCH__) && !defined(RL_COOP_CHOL_SMEM)
+  // Cholesky of M = inv(W) - theta S+ in REGISTERS: lane i < n holds the upper-triangle entries that touch index i
+  // (row[k] = M(min(i,k), max(i,k))), i.e. entry (k, i), k <= i, of the running Schur complement lives in lane i.  Step j:
+  // the pivot comes from lane j and the pivot row's entry (j, k) from lane k by shuffles (issued before the rsqrt, so they
+  // travel under its latency); every lane scales and applies the rank-1 update to its own entries.  No shared-memory round
+  // trip and no warp barrier per pivot; per entry the same operations in the same order as the shared-memory version
+  // below (right-looking, updates in increasing j), hence the same bits.
+  {
+    const unsigned full = 0xffffffffu;
+    const int i = lane < n ? lane : 0;
+    double row[n], crow[n], invs[n];
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      const int a = i < k ? i : k, b = i < k ? k : i;
+      row[k] = rl_fma(-theta, w.S[a + b * n], Winv[a + b * n]);
+      crow[k] = 0.0;
+    }
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const double d = __shfl_sync(full, row[j], j);
+      if (!(d > 0.0)) { bad = 1; break; }
+      double pk[n];
+#pragma unroll
+      for (int k = j + 1; k < n; ++k) pk[k] = __shfl_sync(full, row[j], k);  // M(j, k) lives in lane k
+      detM = (j == 0) ? d : detM * d;
+      const double inv = rl_rsqrt(d);
+      invs[j] = inv;
+      const double ci = row[j] * inv;  // C(i, j) for i > j
+      crow[j] = ci;
+#pragma unroll
+      for (int k = j + 1; k < n; ++k) {
+        const double ck = pk[k] * inv;
+        if (k <= i) row[k] = rl_fma(-ci, ck, row[k]);
+      }
+    }
+    if (bad) return 1;
+    phase(lane, [&](int l) {  // the factor goes where the substitutions below read it
+      if (l < n) {
+#pragma unroll
+        for (int j = 0; j < n; ++j) if (j < l) w.M[l + j * n] = crow[j];
+      }
+      if (l == 0) {
+#pragma unroll
+        for (int j = 0; j < n; ++j) w.invd[j] = invs[j];
+      }
+    });
+  }
+#else
   phase(lane, [&](int l) {
 #pragma unroll
     for (int q = 0; q < (n * n + 31) / 32; ++q) { const int e = l + 32 * q; if (e < n * n) w.M[e] = rl_fma(-theta, w.S[e], Winv[e]); }
@@ -157,7 +207,6 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
   // the factor.  Step j: every lane reads the pivot, scales the column entries it needs itself, and applies the rank-1
   // update to its share of the trailing (k, i) entries (j < k <= i) -- one phase per step instead of a dependent chain of j
   // FMAs per entry.  An entry still receives its updates in increasing j: the rounding sequence of the left-looking form.
-  double detM = 1.0;
   {
     int bad = 0;
 #pragma unroll
@@ -186,6 +235,7 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
     }
     if (bad) return 1;
   }
+#endif
   // forward substitutions, column c of [S+ | s_vec+] per lane, kept in registers; right-looking: once Z[i] is known every
   // later row takes its update at once (the updates of a row still arrive in increasing i: same rounding sequence)
   phase(lane, [&](int l) {
