@@ -115,7 +115,11 @@ static void launch_one(const SolveParams& P, cudaStream_t st) {
         }
 #endif
         if ((size_t)P.B <= (size_t)sms * 384 && !P.queue) launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 64, 4>(P, st);  // + constants pinned in L1
+#if defined(RL_PIN_THROUGHPUT)  // tuning build: the throughput shape with the cost constants on the L1 evict-last path too
+        else launch_shape<D, Cost<RL_COST_QUAD_DIAG_PIN, D::n, D::m>, 128, 3>(P, st);
+#else
         else launch_shape<D, CT, 128, 3>(P, st);   // best of the sweeps in profiles/r01_tune_*.jsonl
+#endif
         return;
       }
     }
