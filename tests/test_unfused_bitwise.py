@@ -36,3 +36,17 @@ def test_unfused_build_is_bit_identical_to_oracle(unfused, oracle_be, coop):
                 assert np.array_equal(a[k][..., ok], b[k][..., ok]), k
     finally:
         unfused.dll.hostemu_set_coop(0)
+
+
+def test_trig_cache_build_is_bit_identical_to_the_default_build(hostemu_be):
+    """-DRL_TRIG_CACHE=1 (opt-in; slower on the power-capped B200, profiles/r02_trig_cache_negative_ab.txt): the unicycle
+    rollout stores (sin psi_k, cos psi_k) of every stage in the workspace record and the backward passes linearise from
+    them.  Same routine, same argument => the same bits as recomputing; checked through the host emulation."""
+    subprocess.check_call(["make", "-C", HERE, "-s", "libhostemu_trigcache.so"])
+    tc = CApi(ctypes.CDLL(os.path.join(HERE, "libhostemu_trigcache.so")), "hostemu_", needs_ctx=False)
+    for prob, x0, u, th in ((*wl.c2_problem(), wl.c2_thetas(48)), (*wl.c2_problem(N=7), [0.0, 0.5, 3.0])):
+        spec = prob.spec()
+        a = hostemu_be.ileqg_solve_batch(spec, x0, u, th, eps_hist_cap=64)
+        b = tc.ileqg_solve_batch(spec, x0, u, th, eps_hist_cap=64)
+        for k in ("status", "iters", "trials", "restarts", "value", "x", "l", "L", "eps_hist", "mu", "d_current"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
