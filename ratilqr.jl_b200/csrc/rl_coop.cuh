@@ -84,11 +84,12 @@ template <class D> struct CoopDyn {
   template <int n, int m> RL_HD static void trig(int, CoopWs<n, m>&) {}
   template <int n, int m> RL_HD static bool f(const double* mp, CoopWs<n, m>& w) { return D::f(mp, w.x, w.u, w.xn); }
 };
-// the quadrotor: sin / cos of the three Euler angles, one libm call per lane (lanes 8..13), instead of twelve calls in the
+// the quadrotor: sin / cos of the three Euler angles, one sincos per lane (lanes 8..10), instead of twelve calls in the
 // lane that steps the dynamics and twenty-four in each of the sixteen lanes that seed a dual-number direction
 template <> struct CoopDyn<Dyn<RATILQR_MODEL_QUADROTOR>> {
   template <int n, int m> RL_HD static void trig(int l, CoopWs<n, m>& w) {
-    if (l >= 8 && l < 14) { const int a = 3 + ((l - 8) >> 1); w.sc[l - 8] = ((l - 8) & 1) ? cos(w.x[a]) : sin(w.x[a]); }
+    // one lane per angle, sin and cos through one branch-free range reduction (the same bits as sin() / cos())
+    if (l >= 8 && l < 11) { const int a = l - 8; rl_sincos_any(w.x[3 + a], &w.sc[2 * a], &w.sc[2 * a + 1]); }
   }
   template <int n, int m> RL_HD static bool f(const double* mp, CoopWs<n, m>& w) { quadrotor_body_sc<double>(mp, w.x, w.u, w.xn, w.sc); return true; }
 };
