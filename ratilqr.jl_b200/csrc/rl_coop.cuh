@@ -81,29 +81,32 @@ RL_HD CoopIO coop_io(const CoopTraj& tj, int buf, int n, int m, int N) {
 // evaluation (lanes 8.. are free there) -- values every lane of the next phase shares; f(): the dynamics step, run by
 // one lane.  Default: nothing to share.
 template <class D> struct CoopDyn {
-  template <int n, int m> RL_HD static void trig(int, CoopWs<n, m>&) {}
+  template <int n, int m> RL_HD static void trig(int, CoopWs<n, m>&, const double*) {}
   template <int n, int m> RL_HD static bool f(const double* mp, CoopWs<n, m>& w) { return D::f(mp, w.x, w.u, w.xn); }
 };
 // the quadrotor: sin / cos of the three Euler angles, one sincos per lane (lanes 8..10), instead of twelve calls in the
 // lane that steps the dynamics and twenty-four in each of the sixteen lanes that seed a dual-number direction
 template <> struct CoopDyn<Dyn<RATILQR_MODEL_QUADROTOR>> {
-  template <int n, int m> RL_HD static void trig(int l, CoopWs<n, m>& w) {
+  template <int n, int m> RL_HD static void trig(int l, CoopWs<n, m>& w, const double* x) {  // x: the state (w.x or its source)
     // one lane per angle, sin and cos through one branch-free range reduction (the same bits as sin() / cos())
-    if (l >= 8 && l < 11) { const int a = l - 8; rl_sincos_any(w.x[3 + a], &w.sc[2 * a], &w.sc[2 * a + 1]); }
+    if (l >= 8 && l < 11) { const int a = l - 8; rl_sincos_any(x[3 + a], &w.sc[2 * a], &w.sc[2 * a + 1]); }
   }
   template <int n, int m> RL_HD static bool f(const double* mp, CoopWs<n, m>& w) { quadrotor_body_sc<double>(mp, w.x, w.u, w.xn, w.sc); return true; }
 };
 
 // models whose Jacobian comes from duals evaluate one seeded direction per lane
+// `extra(l)` runs in the same phase (the stage cost, on a lane the Jacobian leaves free: lane 16)
 template <class D> struct CoopJac {
-  template <int n, int m>
-  RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w) {
-    phase(lane, [&](int l) { if (l == 1) D::jac(mp, w.x, w.u, w.A, w.B); });
+  template <int n, int m, class Extra>
+  RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w, Extra extra) {
+    phase(lane, [&](int l) { extra(l); if (l == 1) D::jac(mp, w.x, w.u, w.A, w.B); });
   }
 };
-template <class Body, int n, int m>
-RL_HD void coop_dual_jac(int lane, Body body, const double* mp, CoopWs<n, m>& w) {
+template <class Body, int n, int m, class Extra>
+RL_HD void coop_dual_jac(int lane, Body body, const double* mp, CoopWs<n, m>& w, Extra extra) {
+  static_assert(n + m <= 16, "lane 16 runs the extra job of the phase");
   phase(lane, [&](int l) {
+    extra(l);
     if (l >= n + m) return;
     Dual<1> xd[n], ud[m], xo[n];
     for (int i = 0; i < n; ++i) { xd[i].v = w.x[i]; xd[i].d[0] = (i == l) ? 1.0 : 0.0; }
@@ -113,16 +116,16 @@ RL_HD void coop_dual_jac(int lane, Body body, const double* mp, CoopWs<n, m>& w)
   });
 }
 template <> struct CoopJac<Dyn<RATILQR_MODEL_CARTPOLE>> {
-  template <int n, int m> RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w) { coop_dual_jac(lane, CartpoleBody(), mp, w); }
+  template <int n, int m, class Extra> RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w, Extra extra) { coop_dual_jac(lane, CartpoleBody(), mp, w, extra); }
 };
 struct QuadrotorBodySc {  // the body with the shared trigonometry of CoopDyn<quadrotor>::trig
   const double* sc;
   template <class T> RL_HD void operator()(const double* p, const T* x, const T* u, T* xn) const { quadrotor_body_sc<T>(p, x, u, xn, sc); }
 };
 template <> struct CoopJac<Dyn<RATILQR_MODEL_QUADROTOR>> {
-  template <int n, int m> RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w) {
+  template <int n, int m, class Extra> RL_HD static void run(int lane, const double* mp, CoopWs<n, m>& w, Extra extra) {
     QuadrotorBodySc body; body.sc = w.sc;
-    coop_dual_jac(lane, body, mp, w);
+    coop_dual_jac(lane, body, mp, w, extra);
   }
 };
 
@@ -676,22 +679,24 @@ RL_HD int coop_backward_pass(int lane, const SolveParams& P, const double* cp, d
     for (int k = N - 1; k >= 0; --k) {
       const double* Lrk = io.Lr + (size_t)k * m * n;
       double* Lwk = io.Lw + (size_t)k * m * n;
+      // two phases: [operands into the workspace | the model's trigonometry straight from the trajectory] and
+      // [Jacobian (lanes 0 .. n+m-1, or lane 1) | stage cost (lane 16)] -- pure functions, so running the Jacobian beside a
+      // cost evaluation that ends in a domain error is harmless
       phase(lane, [&](int l) {
+        CoopDyn<D>::trig(l, w, Xb + (size_t)k * n);
         for (int e = l; e < n + m + m * n; e += 32) {
           if (e < n) w.x[e] = Xb[(size_t)k * n + e];
           else if (e < n + m) w.u[e - n] = Ub[(size_t)k * m + (e - n)];
           else if (!OPT) w.L[e - n - m] = zeroL ? 0.0 : Lrk[e - n - m];
         }
       });
-      phase(lane, [&](int l) {
-        CoopDyn<D>::trig(l, w);
-        if (l != 0) return;
+      CoopJac<D>::run(lane, P.mp, w, [&](int l) {
+        if (l != 16) return;
         double q;
         w.flag = CT::stage(cp, k, w.x, w.u, true, q, w.qv, w.Q, w.r, w.R, w.Pm) ? 0.0 : 1.0;
         w.q = q;
       });
       if (w.flag != 0.0) return RATILQR_ST_DOMAIN;
-      CoopJac<D>::run(lane, P.mp, w);
       const size_t wo = P.W_tv ? (size_t)k * n * n : 0;
       int rc = coop_riccati_stage<Tr, OPT, OPT>(lane, w, theta, mu, P.W + wo, P.Winv + wo, P.detW[P.W_tv ? k : 0], s, RL_FUSED ? &detprod : nullptr);
       if (rc == 1) return OPT ? RATILQR_ST_M_NOT_PD_OPT : RATILQR_ST_M_NOT_PD_INIT;
@@ -736,7 +741,7 @@ RL_HD int coop_rollout(int lane, const SolveParams& P, const CoopIO& io, double 
   for (int k = 0; k < N; ++k) {
     const double* Lk = io.Lr + (size_t)k * m * n;
     phase(lane, [&](int l) {
-      CoopDyn<D>::trig(l, w);
+      CoopDyn<D>::trig(l, w, w.x);
       for (int j = l; j < m; j += 32) {
         const double lj = Uc[(size_t)k * m + j];
         double uj = lj;
