@@ -26,6 +26,10 @@ RL_HD void phase(int lane, F&& f) {
 #endif
 }
 
+// compile-time switches handed to generic lambdas
+struct CoopTagFast { static constexpr bool value = true; };
+struct CoopTagLib { static constexpr bool value = false; };
+
 // shared-memory workspace of one warp (doubles)
 template <int n, int m>
 struct CoopWs {
@@ -157,38 +161,56 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
 #if defined(__CUDA_ARCH__) && !defined(RL_COOP_CHOL_SMEM)
   // Cholesky of M = inv(W) - theta S+ in REGISTERS: lane i < n holds the upper-triangle entries that touch index i
   // (row[k] = M(min(i,k), max(i,k))), i.e. entry (k, i), k <= i, of the running Schur complement lives in lane i.  Step j:
-  // the pivot comes from lane j and the pivot row's entry (j, k) from lane k by shuffles (issued before the rsqrt, so they
-  // travel under its latency); every lane scales and applies the rank-1 update to its own entries.  No shared-memory round
+  // the pivot row's entry (j, k) comes from lane k by shuffles (issued before the rsqrt, so they travel under its
+  // latency); every lane scales and applies the rank-1 update to its own entries.  No shared-memory round
   // trip and no warp barrier per pivot; per entry the same operations in the same order as the shared-memory version
   // below (right-looking, updates in increasing j), hence the same bits.
   {
     const unsigned full = 0xffffffffu;
     const int i = lane < n ? lane : 0;
-    double row[n], crow[n], invs[n];
+    double row[n], crow[n], invs[n], diag[n];
+    auto load = [&]() {
 #pragma unroll
-    for (int k = 0; k < n; ++k) {
-      const int a = i < k ? i : k, b = i < k ? k : i;
-      row[k] = rl_fma(-theta, w.S[a + b * n], Winv[a + b * n]);
-      crow[k] = 0.0;
-    }
-    int bad = 0;
-#pragma unroll
-    for (int j = 0; j < n; ++j) {
-      const double d = __shfl_sync(full, row[j], j);
-      if (!(d > 0.0)) { bad = 1; break; }
-      double pk[n];
-#pragma unroll
-      for (int k = j + 1; k < n; ++k) pk[k] = __shfl_sync(full, row[j], k);  // M(j, k) lives in lane k
-      detM = (j == 0) ? d : detM * d;
-      const double inv = rl_rsqrt(d);
-      invs[j] = inv;
-      const double ci = row[j] * inv;  // C(i, j) for i > j
-      crow[j] = ci;
-#pragma unroll
-      for (int k = j + 1; k < n; ++k) {
-        const double ck = pk[k] * inv;
-        if (k <= i) row[k] = rl_fma(-ci, ck, row[k]);
+      for (int k = 0; k < n; ++k) {
+        const int a = i < k ? i : k, b = i < k ? k : i;
+        row[k] = rl_fma(-theta, w.S[a + b * n], Winv[a + b * n]);
+        crow[k] = 0.0;
+        // every lane also tracks the whole running DIAGONAL (the same fma lane k applies to its entry (k, k)): the next
+        // pivot is then a local value and no shuffle sits on the pivot -> rsqrt -> scale -> update chain of the factorisation
+        diag[k] = rl_fma(-theta, w.S[k + k * n], Winv[k + k * n]);
       }
+    };
+    load();
+    // positive-definiteness and the library rsqrt's slow-path test are recorded and acted on after the loop (a failed
+    // pivot only poisons values nobody uses): the factorisation is one basic block.  A pivot that needs the slow path
+    // (denormal / Inf) re-runs the loop through the library routine.
+    bool bad = false, slow = false;
+    auto factor = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        const double d = diag[j];
+        bad = bad || !(d > 0.0);
+        double pk[n];
+#pragma unroll
+        for (int k = j + 1; k < n; ++k) pk[k] = __shfl_sync(full, row[j], k);  // M(j, k) lives in lane k
+        detM = (j == 0) ? d : detM * d;
+        const double inv = FAST ? rl_rsqrt_nb(d, slow) : rl_rsqrt(d);
+        invs[j] = inv;
+        const double ci = row[j] * inv;  // C(i, j) for i > j
+        crow[j] = ci;
+#pragma unroll
+        for (int k = j + 1; k < n; ++k) {
+          const double ck = pk[k] * inv;
+          diag[k] = rl_fma(-ck, ck, diag[k]);
+          if (k <= i) row[k] = rl_fma(-ci, ck, row[k]);
+        }
+      }
+    };
+    factor(CoopTagFast());
+    if (!bad && slow) {  // (warp-uniform: every lane sees the same pivots)
+      load();
+      factor(CoopTagLib());
     }
     if (bad) return 1;
     phase(lane, [&](int l) {  // the factor goes where the substitutions below read it
