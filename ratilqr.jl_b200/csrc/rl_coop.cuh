@@ -350,25 +350,36 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
   });
   if (OPT) {
     // Cholesky of H (m x m, tiny): every lane factors it redundantly in registers -- no phases, the same operations
+    // (device: the pivots' tests are recorded and acted on after the loop, branch-free rsqrt with the library routine on
+    // its slow-path flag -- as in the factorisation of M above)
     double ch[m * m], ih[m];
     {
-      int bad = 0;
+      bool bad = false, slow = false;
+      auto factor = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
-      for (int j = 0; j < m; ++j) {
-        double d = w.H[j + j * m];
+        for (int j = 0; j < m; ++j) {
+          double d = w.H[j + j * m];
 #pragma unroll
-        for (int k = 0; k < j; ++k) d = rl_fma(-ch[j + k * m], ch[j + k * m], d);
-        if (!(d > 0.0)) { bad = 1; break; }
-        const double inv = rl_rsqrt(d);
-        ih[j] = inv;
+          for (int k = 0; k < j; ++k) d = rl_fma(-ch[j + k * m], ch[j + k * m], d);
+          bad = bad || !(d > 0.0);
+          const double inv = FAST ? rl_rsqrt_nb(d, slow) : rl_rsqrt(d);
+          ih[j] = inv;
 #pragma unroll
-        for (int i = j + 1; i < m; ++i) {
-          double a = w.H[j + i * m];
+          for (int i = j + 1; i < m; ++i) {
+            double a = w.H[j + i * m];
 #pragma unroll
-          for (int k = 0; k < j; ++k) a = rl_fma(-ch[i + k * m], ch[j + k * m], a);
-          ch[i + j * m] = a * inv;
+            for (int k = 0; k < j; ++k) a = rl_fma(-ch[i + k * m], ch[j + k * m], a);
+            ch[i + j * m] = a * inv;
+          }
         }
-      }
+      };
+#if defined(__CUDA_ARCH__)
+      factor(CoopTagFast());
+      if (!bad && slow) factor(CoopTagLib());
+#else
+      factor(CoopTagLib());
+#endif
       if (bad) return 2;
     }
     phase(lane, [&](int l) {  // L = -H\G (column c per lane), dl = -H\g (column n)
