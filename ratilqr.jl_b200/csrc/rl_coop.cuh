@@ -36,7 +36,7 @@ struct CoopWs {
   double S[n * n], sv[n], M[n * n], invd[n], Z[n * n], z[n], DS[n * n], Dsv[n];
   double A[n * n], B[n * m], Q[n * n], R[m * m], Pm[m * n], qv[n], r[m];
   double T[n * n], U[n * m], g[m], G[m * n], H[m * m], CH[m * m], invh[m], L[m * n], dl[m], HL[m * n], Hdl[m];
-  double x[n], u[m], xn[n], Sn[n * n], svn[n];
+  double x[n], u[m], xn[n];
   double q, flag, nrm;  // stage cost value; domain-error flag; ||l - u||^2 of the rollout step
   double sc[8];         // per-stage trigonometry shared by the lanes (CoopDyn<quadrotor>)
   double V[m * n], Hdlg[m];  // H L + G and H dl + g (dense stage)
@@ -411,13 +411,14 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
     for (int q = 0; q < NE; ++q) {
       const int e = l + 32 * q, ee = e < TOT ? e : 0;
       const int i = ee < m * n ? ee % m : ee - m * n;
-      xa[q] = w.H + i; xb[q] = ee < m * n ? w.L + (ee / m) * m : w.dl; acc[q] = 0.0; start[q] = true;
+      xa[q] = w.H + i; xb[q] = ee < m * n ? w.L + (ee / m) * m : w.dl;
+      start[q] = !(ee < m * n); acc[q] = start[q] ? 0.0 : w.G[ee];  // V accumulates onto G (rl::riccati_stage, fused order)
     }
     lane_dots<m, NE>([&](int q, int k, double& a, double& b) { a = xa[q][k * m]; b = xb[q][k]; }, start, acc);
 #pragma unroll
     for (int q = 0; q < NE; ++q) {
       const int e = l + 32 * q;
-      if (e < m * n) { w.HL[e] = acc[q]; w.V[e] = acc[q] + w.G[e]; }
+      if (e < m * n) w.V[e] = acc[q];
       else if (e < TOT) { w.Hdl[e - m * n] = acc[q]; w.Hdlg[e - m * n] = acc[q] + w.g[e - m * n]; }
     }
   });
@@ -428,7 +429,7 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
     sval = dot_acc<m>(rl_fma(0.5, a, sval), w.dl, 1, w.g, 1);
   }
   s = sval + extra;
-  phase(lane, [&](int l) {  // s_vec and S (upper triangle, mirrored) into the double buffers
+  phase(lane, [&](int l) {  // s_vec and S (upper triangle, mirrored)
     constexpr int NS = n * (n + 1) / 2, TOT = n + NS, NE = (TOT + 31) / 32;
     const double* xa[NE]; const double* xb[NE]; double acc[NE]; bool start[NE]; int oi[NE], oj[NE];
 #pragma unroll
@@ -459,14 +460,10 @@ RL_HD int coop_riccati_stage_dense(int lane, CoopWs<Tr::n, Tr::m>& w, double the
 #pragma unroll
     for (int q = 0; q < NE; ++q) {
       const int e = l + 32 * q;
-      if (e < n) w.svn[e] = acc[q];
-      else if (e < TOT) { w.Sn[oi[q] + oj[q] * n] = acc[q]; w.Sn[oj[q] + oi[q] * n] = acc[q]; }
+      // straight into S / s_vec: nothing in this phase reads them any more (S+ and s_vec+ were last used for D S+, D s_vec+)
+      if (e < n) w.sv[e] = acc[q];
+      else if (e < TOT) { w.S[oi[q] + oj[q] * n] = acc[q]; w.S[oj[q] + oi[q] * n] = acc[q]; }
     }
-  });
-  phase(lane, [&](int l) {
-#pragma unroll
-    for (int q = 0; q < (n * n + 31) / 32; ++q) { const int e = l + 32 * q; if (e < n * n) w.S[e] = w.Sn[e]; }
-    for (int e = l; e < n; e += 32) w.sv[e] = w.svn[e];
   });
   return 0;
 }
@@ -613,6 +610,7 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
     for (int e = l; e < m * n + (HAS_DL ? m : 0); e += 32) {
       if (e < m * n) {
         int i = e % m, j = e / m;
+        if (RL_FUSED) { w.HL[e] = dot_acc<m>(w.G[e], w.H + i, m, w.L + j * m, 1); continue; }  // V = H L + G (fused order)
         double a = w.H[i] * w.L[j * m];
         for (int k = 1; k < m; ++k) a = rl_fma(w.H[i + k * m], w.L[k + j * m], a);
         w.HL[e] = a;
@@ -631,7 +629,7 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
     else { double b = w.dl[0] * w.g[0]; for (int k = 1; k < m; ++k) b = rl_fma(w.dl[k], w.g[k], b); sval = (sval + 0.5 * a) + b; }
   }
   s = sval + extra;
-  phase(lane, [&](int l) {  // s_vec and S (upper), into the double buffers
+  phase(lane, [&](int l) {  // s_vec and S (upper); nothing in this phase reads S+ / s_vec+ any more
     for (int e = l; e < n + n * n; e += 32) {
       if (e < n) {
         int i = e;
@@ -640,7 +638,7 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
           if (HAS_DL) { double t[m]; for (int k = 0; k < m; ++k) t[k] = w.Hdl[k] + w.g[k]; acc = dot_acc<m>(acc, w.L + i * m, 1, t, 1); }
           else acc = dot_acc<m>(acc, w.L + i * m, 1, w.g, 1);
           if (HAS_DL) acc = dot_acc<m>(acc, w.G + i * m, 1, w.dl, 1);
-          w.svn[i] = acc;
+          w.sv[i] = acc;
           continue;
         }
         double acc = w.qv[i] + coldot<Tr, KindA, n>(w.A, i, w.Dsv, 1);
@@ -648,16 +646,16 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
         double c = w.L[i * m] * w.g[0]; for (int k = 1; k < m; ++k) c = rl_fma(w.L[k + i * m], w.g[k], c);
         acc = acc + c;
         if (HAS_DL) { double d = w.G[i * m] * w.dl[0]; for (int k = 1; k < m; ++k) d = rl_fma(w.G[k + i * m], w.dl[k], d); acc = acc + d; }
-        w.svn[i] = acc;
+        w.sv[i] = acc;
       } else {
         int f = e - n, i = f % n, j = f / n;
         if (j < i) continue;
         if (RL_FUSED) {
           double acc = (Tr::q_kind(i, j) == 0) ? coldot<Tr, KindA, n>(w.A, i, w.T + j * n, 1) : coldot_acc<Tr, KindA, n>(w.Q[i + j * n], w.A, i, w.T + j * n, 1);
-          { double t[m]; for (int k = 0; k < m; ++k) t[k] = w.HL[k + j * m] + w.G[k + j * m]; acc = dot_acc<m>(acc, w.L + i * m, 1, t, 1); }
+          acc = dot_acc<m>(acc, w.L + i * m, 1, w.HL + j * m, 1);  // L'(H L + G): w.HL holds V in the fused order
           acc = dot_acc<m>(acc, w.G + i * m, 1, w.L + j * m, 1);
-          w.Sn[i + j * n] = acc;
-          w.Sn[j + i * n] = acc;
+          w.S[i + j * n] = acc;
+          w.S[j + i * n] = acc;
           continue;
         }
         double a = coldot<Tr, KindA, n>(w.A, i, w.T + j * n, 1);
@@ -668,14 +666,10 @@ RL_HD int coop_riccati_stage(int lane, CoopWs<Tr::n, Tr::m>& w, double theta, do
         acc = acc + c;
         double d = w.G[i * m] * w.L[j * m]; for (int k = 1; k < m; ++k) d = rl_fma(w.G[k + i * m], w.L[k + j * m], d);
         acc = acc + d;
-        w.Sn[i + j * n] = acc;
-        w.Sn[j + i * n] = acc;
+        w.S[i + j * n] = acc;
+        w.S[j + i * n] = acc;
       }
     }
-  });
-  phase(lane, [&](int l) {
-    for (int e = l; e < n * n; e += 32) w.S[e] = w.Sn[e];
-    for (int e = l; e < n; e += 32) w.sv[e] = w.svn[e];
   });
   return 0;
 }

@@ -50,3 +50,22 @@ def test_trig_cache_build_is_bit_identical_to_the_default_build(hostemu_be):
         b = tc.ileqg_solve_batch(spec, x0, u, th, eps_hist_cap=64)
         for k in ("status", "iters", "trials", "restarts", "value", "x", "l", "L", "eps_hist", "mu", "d_current"):
             assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_cooperative_formulation_is_bit_identical_to_thread_per_instance(hostemu_be):
+    """DESIGN: every output element of the warp-cooperative stage is accumulated by one lane in the order the thread-per-
+    instance stage uses, so the two formulations of the SHIPPED (fused) arithmetic agree bit for bit -- structured small
+    models (rolled cooperative stage) and a dense one (restructured stage), through the host emulation."""
+    cases = [(*wl.c1_problem(), [0.0, 0.1, 0.43, 30.7]), (*wl.c2_problem(N=12), wl.c2_thetas(24))]
+    prob, x0, u = wl.c3_problem(N=6)
+    cases.append((prob, x0, u, [0.0, 0.02]))
+    for prob, x0, u, th in cases:
+        spec = prob.spec()
+        a = hostemu_be.ileqg_solve_batch(spec, x0, u, th, eps_hist_cap=64)
+        hostemu_be.dll.hostemu_set_coop(1)
+        try:
+            b = hostemu_be.ileqg_solve_batch(spec, x0, u, th, eps_hist_cap=64)
+        finally:
+            hostemu_be.dll.hostemu_set_coop(0)
+        for k in ("status", "iters", "trials", "restarts", "value", "x", "l", "L", "eps_hist", "mu"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
